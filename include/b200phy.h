@@ -1,0 +1,236 @@
+/*
+ * b200phy.h — C ABI of libb200phy.so: the B200-native (sm_100a) implementation of
+ * pyphysim's per-realization link hot path.
+ *
+ * The reference (darcamo/pyphysim) has no FFI layer: its boundary is the Python
+ * class API.  Each entry point below names the reference method(s) it replaces
+ * (paths relative to the reference repo root).  The Python façade package
+ * `pyphysim_b200` binds these symbols with ctypes; INTEGRATION.md shows the stub a
+ * maintainer would add to the reference itself.
+ *
+ * Conventions
+ *   - Every pointer argument marked "dev" is a CUDA device pointer; "host" is a
+ *     host pointer.  No C++/torch types cross this boundary.
+ *   - `dtype` selects the arithmetic: B200PHY_F32 (complex64 samples, interleaved
+ *     re,im floats) or B200PHY_F64 (complex128).  Small linear solves always run in
+ *     double.  Symbol indices are int64 in the stage ops (reference dtype) and
+ *     uint8 in the fused link ops (M <= 256).
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream).  All work
+ *     is enqueued on it; nothing synchronises unless documented.
+ *   - Return value: 0 on success, otherwise a B200PHY_ERR_* code;
+ *     b200phy_last_error() gives the message (thread-local).
+ *   - counters: int64[4] = {symbol_errors, bit_errors, num_symbols, num_bits},
+ *     ACCUMULATED in place (zero them before a new SNR point).
+ *   - Random draws follow the shared Philox4x32-10 contract (oracle/philox.py,
+ *     pyphysim_b200/csrc/rng.cuh): a pure function of (seed, stream, unit, word),
+ *     unit = global realization / frame index, so results are invariant to batch
+ *     size and to how units are sharded over GPUs.
+ */
+#ifndef B200PHY_H
+#define B200PHY_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200PHY_VERSION 100
+
+enum { B200PHY_F32 = 0, B200PHY_F64 = 1 };
+
+/* demap kinds */
+enum {
+    B200PHY_MODEM_TABLE = 0, /* arbitrary table: argmin_m |s_m - r|, first minimum wins
+                                (Modulator.demodulate, modulators/fundamental.py:241-248) */
+    B200PHY_MODEM_QAM = 1,   /* square Gray QAM built by QAM.__init__ (fundamental.py:659-777):
+                                per-axis slicer, identical decisions to the table search */
+    B200PHY_MODEM_BPSK = 2   /* BPSK.modulate/demodulate (fundamental.py:605-647) */
+};
+
+enum {
+    B200PHY_OK = 0,
+    B200PHY_ERR_INVALID = 1,     /* bad argument (the façade maps these to ValueError) */
+    B200PHY_ERR_UNSUPPORTED = 2, /* shape outside what the kernels are built for */
+    B200PHY_ERR_CUDA = 3,        /* CUDA runtime error */
+    B200PHY_ERR_RANGE = 4        /* symbol index >= M seen on the device (-> ValueError,
+                                    fundamental.py:196-199) */
+};
+
+#define B200PHY_MAX_TAPS 32
+#define B200PHY_MAX_RAYS 64
+#define B200PHY_MAX_ANT 4
+
+/* Jakes evaluation strategies of the fused OFDM/TDL kernel */
+enum {
+    B200PHY_JAKES_AUTO = 0,     /* polynomial when its error bound holds, else recurrence */
+    B200PHY_JAKES_RECURRENCE = 1,
+    B200PHY_JAKES_POLY = 2
+};
+
+typedef struct b200phy_modem {
+    int32_t kind;      /* B200PHY_MODEM_* */
+    int32_t M;         /* constellation size, power of two, <= 256 */
+    const void *table; /* dev: M complex values of the call's dtype (Modulator.symbols) */
+} b200phy_modem;
+
+/* One OFDM frame over a Jakes/TDL channel (notebooks/TDL_and_OFDM.ipynb cell 32; MIMO
+ * variant = Blast.encode -> OFDM.modulate per tx antenna -> TdlMimoChannel.corrupt_data ->
+ * OFDM.demodulate per rx antenna -> per-subcarrier Blast.decode). */
+typedef struct b200phy_ofdm_tdl_params {
+    int32_t struct_size;  /* sizeof(b200phy_ofdm_tdl_params), for ABI checking */
+    int32_t dtype;        /* B200PHY_F32 / B200PHY_F64 */
+    int32_t fft, cp, used, n_sym; /* OFDM(fft, cp, used) (modulators/ofdm.py:20-94); OFDM symbols/frame */
+    int32_t Nr, Nt;       /* 1x1: one-tap equaliser (ofdm.py:469-552); else Blast (mimo/mimo.py:465-660) */
+    int32_t n_taps;       /* discretised profile (channels/fading.py:272-304) */
+    int32_t L;            /* Jakes rays (channels/fading_generators.py:319-351) */
+    int32_t jakes_mode;   /* B200PHY_JAKES_* */
+    int32_t reserved;
+    int32_t delays[B200PHY_MAX_TAPS];    /* tap delays in samples, increasing */
+    double tap_powers[B200PHY_MAX_TAPS]; /* linear tap powers */
+    double Fd, Ts, t0;    /* Doppler [Hz], sample time [s], time of the frame's first sample */
+    double noise_var;     /* AWGN variance per rx sample (1/dB2Linear(SNR)) */
+    double filter_noise_var; /* Blast.set_noise_var value: >0 MMSE, 0 ZF (mimo.py:597-605) */
+    uint64_t seed;        /* Philox key */
+} b200phy_ofdm_tdl_params;
+
+/* ---- library ------------------------------------------------------------------ */
+int b200phy_version(void);
+const char *b200phy_last_error(void);
+/* number of kernels this library has launched in the calling process (bench `gpu_launches`) */
+uint64_t b200phy_launch_count(void);
+
+/* ---- stage ops (API-parity path behind the façade classes) ---------------------- */
+
+/* Modulator.modulate (fundamental.py:175-199), BPSK.modulate (:605-630).
+ * idx dev int64[n] -> out dev complex[n].  err_flag dev int32[1] is set to 1 if any idx >= M
+ * (negative indices wrap like NumPy). */
+int b200phy_map(int dtype, const b200phy_modem *modem, const int64_t *idx, int64_t n, void *out,
+                int32_t *err_flag, void *stream);
+
+/* Modulator.demodulate (fundamental.py:201-248), BPSK.demodulate (:632-647).
+ * r dev complex[n] -> idx_hat dev int64[n]. */
+int b200phy_demap(int dtype, const b200phy_modem *modem, const void *r, int64_t n,
+                  int64_t *idx_hat, void *stream);
+
+/* sum(a != b) and util.misc.count_bit_errors (util/misc.py:519-566) in one pass.
+ * a, b dev int64[n]; out dev int64[2] += {symbol_errors, bit_errors}. */
+int b200phy_count_errors(const int64_t *a, const int64_t *b, int64_t n, int64_t *out,
+                         void *stream);
+
+/* util.misc.count_bits (util/misc.py:449-476): elementwise popcount of non-negative int64. */
+int b200phy_count_bits(const int64_t *a, int64_t n, int64_t *out, void *stream);
+
+/* misc.randn_c * sqrt(noise_var) added in place (util/misc.py:327-355): x[i] += sigma*c_i with c_i
+ * the complex normal `first + i` of (seed, stream_id, unit). */
+int b200phy_awgn(int dtype, void *x, int64_t n, double noise_var, uint64_t seed,
+                 uint32_t stream_id, uint64_t unit, uint64_t first, void *stream);
+
+/* OFDM.modulate (ofdm.py:394-429): x dev complex[batch][n_sym*used] ->
+ * out dev complex[batch][n_sym*(fft+cp)].  (Zero padding to whole symbols is done by the caller.) */
+int b200phy_ofdm_mod(int dtype, const void *x, void *out, int64_t batch, int n_sym, int fft, int cp,
+                     int used, void *stream);
+/* OFDM.demodulate (ofdm.py:431-466): r dev complex[batch][n_sym*(fft+cp)] -> y dev complex[batch][n_sym*used]. */
+int b200phy_ofdm_demod(int dtype, const void *r, void *y, int64_t batch, int n_sym, int fft, int cp,
+                       int used, void *stream);
+
+/* JakesSampleGenerator.generate_more_samples (fading_generators.py:495-523).
+ * phi, psi dev real[L][P]; h dev complex[P][N]; t_n = t0 + n*Ts*1.0000000001 (:459-467). */
+int b200phy_jakes(int dtype, const void *phi, const void *psi, int L, int64_t P, int64_t N, double Fd,
+                  double Ts, double t0, void *h, void *stream);
+
+/* TdlChannel.corrupt_data (channels/fading.py:1046-1124), forward direction.
+ * x dev complex[Nt][N]; fading dev complex[n_taps][Nr][Nt][N] (unit-power Jakes/Rayleigh samples);
+ * y dev complex[Nr][N+mem], mem = delays[n_taps-1].  tap_powers host double[n_taps] (linear),
+ * delays host int32[n_taps]. */
+int b200phy_tdl_apply(int dtype, const void *x, const void *fading, const double *tap_powers,
+                      const int32_t *delays, int n_taps, int Nr, int Nt, int64_t N, void *y,
+                      void *stream);
+
+/* OfdmOneTapEqualizer.equalize_data (ofdm.py:515-552) restated as FFT(mean taps):
+ * y dev complex[Nr][n_sym*used]; fading as in b200phy_tdl_apply with N = n_sym*(fft+cp);
+ * out dev complex[Nt*n_sym*used]: 1x1 -> y/H; otherwise per-subcarrier Blast decode
+ * (filter_noise_var > 0: MMSE, else ZF; mimo.py:264-309, 590-660), layer-interleaved. */
+int b200phy_ofdm_equalize(int dtype, const void *y, const void *fading, const double *tap_powers,
+                          const int32_t *delays, int n_taps, int Nr, int Nt, int n_sym, int fft,
+                          int cp, int used, double filter_noise_var, void *out, void *stream);
+
+/* Blast.decode (mimo.py:642-660) for a batch of channels: H dev complex[batch][Nr][Nt],
+ * y dev complex[batch][Nr][T] -> out dev complex[batch][Nt*T] (order='F' interleave). */
+int b200phy_blast_decode(int dtype, const void *H, const void *y, int64_t batch, int Nr, int Nt,
+                         int T, double filter_noise_var, void *out, void *stream);
+
+/* Alamouti.encode (mimo.py:1166-1214): s dev complex[batch][T] -> x dev complex[batch][2][T]. */
+int b200phy_alamouti_encode(int dtype, const void *s, int64_t batch, int T, void *x, void *stream);
+/* Alamouti.decode (mimo.py:1216-1287): H dev complex[batch][Nr][2], y dev complex[batch][Nr][T]
+ * -> out dev complex[batch][T]. */
+int b200phy_alamouti_decode(int dtype, const void *H, const void *y, int64_t batch, int Nr, int T,
+                            void *out, void *stream);
+
+/* ---- fused link ops (throughput path) ------------------------------------------
+ * Each covers realizations/frames [first_unit, first_unit + n_units).  Draw arrays are
+ * "stream mode" inputs; pass them all NULL for "fused mode" (in-kernel Philox).
+ * idx_hat / dec_out are optional outputs (NULL to skip). */
+
+/* 1 symbol per realization: r = h*x + sqrt(noise_var)*n; r /= h
+ * (notebooks/Transmission_with_Rayleigh_and_AWGN_channels.ipynb cell 8; rayleigh=0 is the AWGN
+ * chain of apps/awgn_modulators/simulate_psk.py:51-115).
+ * idx dev uint8[n], h dev complex[n] (ignored if !rayleigh), noise dev complex[n]. */
+int b200phy_link_siso_flat(int dtype, const b200phy_modem *modem, int rayleigh, double noise_var,
+                           uint64_t seed, uint64_t first_unit, int64_t n_units, const uint8_t *idx,
+                           const void *h, const void *noise, uint8_t *idx_hat, void *dec_out,
+                           int64_t *counters, void *stream);
+
+/* Alamouti over flat Rayleigh (apps/mimo/simulate_mimo.py:68-142 with mimo.Alamouti):
+ * per realization H[Nr][2], S symbols (even).  idx dev uint8[n][S], H dev complex[n][Nr][2],
+ * noise dev complex[n][Nr][S]. */
+int b200phy_link_alamouti(int dtype, const b200phy_modem *modem, int Nr, int S, double noise_var,
+                          uint64_t seed, uint64_t first_unit, int64_t n_units, const uint8_t *idx,
+                          const void *H, const void *noise, uint8_t *idx_hat, void *dec_out,
+                          int64_t *counters, void *stream);
+
+/* Blast ZF/MMSE over flat Rayleigh (simulate_mimo.py:68-142 with mimo.Blast): S symbol vectors per
+ * realization.  idx dev uint8[n][S*Nt], H dev complex[n][Nr][Nt], noise dev complex[n][Nr][S]. */
+int b200phy_link_blast(int dtype, const b200phy_modem *modem, int Nr, int Nt, int S, double noise_var,
+                       double filter_noise_var, uint64_t seed, uint64_t first_unit, int64_t n_units,
+                       const uint8_t *idx, const void *H, const void *noise, uint8_t *idx_hat,
+                       void *dec_out, int64_t *counters, void *stream);
+
+/* OFDM over Jakes/TDL, SISO or Blast-MIMO (see b200phy_ofdm_tdl_params).
+ * idx dev uint8[n][Nt*n_sym*used]; phi, psi dev real[n][L][n_taps][Nr][Nt];
+ * noise dev complex[n][Nr][N+mem] (unit variance), N = n_sym*(fft+cp);
+ * idx_hat dev uint8 like idx; eq_out dev complex[n][Nt*n_sym*used] (equalised symbols). */
+int b200phy_link_ofdm_tdl(const b200phy_ofdm_tdl_params *p, const b200phy_modem *modem,
+                          uint64_t first_unit, int64_t n_units, const uint8_t *idx, const void *phi,
+                          const void *psi, const void *noise, uint8_t *idx_hat, void *eq_out,
+                          int64_t *counters, void *stream);
+
+/* ---- draw dumps: write the fused-mode Philox draws in the stream-mode layouts, so the oracle can
+ * consume literally the numbers the device used.  NULL outputs are skipped. */
+int b200phy_draw_siso_flat(int dtype, int bits, uint64_t seed, uint64_t first_unit, int64_t n_units,
+                           uint8_t *idx, void *h, void *noise, void *stream);
+int b200phy_draw_flat_mimo(int dtype, int bits, int Nr, int Nt, int S, int n_data, uint64_t seed,
+                           uint64_t first_unit, int64_t n_units, uint8_t *idx, void *H, void *noise,
+                           void *stream);
+int b200phy_draw_ofdm_tdl(const b200phy_ofdm_tdl_params *p, int bits, uint64_t first_unit,
+                          int64_t n_units, uint8_t *idx, void *phi, void *psi, void *noise,
+                          void *stream);
+
+/* ---- host-buffer entry points (what a non-CUDA caller binds; `e2e` in bench.py) -------------
+ * Same semantics as the device versions but every array is a HOST pointer (pinned memory makes the
+ * copies asynchronous); the library stages chunks through its own device buffers, overlapping
+ * H2D, compute and D2H on internal streams, and returns after the results are in host memory.
+ * counters is host int64[4], accumulated. */
+int b200phy_link_siso_flat_host(int dtype, int modem_kind, int M, const double *table_re_im,
+                                int rayleigh, double noise_var, uint64_t seed, uint64_t first_unit,
+                                int64_t n_units, const uint8_t *idx, const void *h,
+                                const void *noise, uint8_t *idx_hat, int64_t *counters);
+int b200phy_link_ofdm_tdl_host(const b200phy_ofdm_tdl_params *p, int modem_kind, int M,
+                               const double *table_re_im, uint64_t first_unit, int64_t n_units,
+                               const uint8_t *idx, const void *phi, const void *psi,
+                               const void *noise, uint8_t *idx_hat, int64_t *counters);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200PHY_H */

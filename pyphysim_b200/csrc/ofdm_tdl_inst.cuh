@@ -1,0 +1,75 @@
+// ofdm_tdl_inst.cuh — defines launch_ofdm_tdl<B200_NR, B200_NT>; included by one .cu per antenna
+// configuration so the (large) kernel instantiations compile in parallel.
+#include "ofdm_tdl.cuh"
+
+namespace b200phy {
+
+template <typename T, bool FUSED, int NR, int NT, bool WSG>
+static int launch_one(const OfdmP &p, const Modem &m, const void *table, uint64_t first_unit,
+                      int64_t n_units, const uint8_t *idx, const void *phi, const void *psi,
+                      const void *noise, uint8_t *idx_hat, void *eq_out, int64_t *counters,
+                      size_t smem, cudaStream_t st) {
+    auto kern = ofdm_tdl_kernel<T, FUSED, NR, NT, WSG>;
+    int e = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)),
+                       "cudaFuncSetAttribute(ofdm_tdl_kernel)");
+    if (e) return e;
+    int dev = 0, sms = 148, occ = 1;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    e = check_cuda(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kOT, smem),
+                   "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
+    if (e) return e;
+    if (occ < 1) { set_error("ofdm_tdl_kernel does not fit on an SM (%zu B shared memory)", smem); return B200PHY_ERR_UNSUPPORTED; }
+    long long grid = (long long)sms * occ;
+    if (grid > n_units) grid = n_units;
+    cx<T> *ws = nullptr;
+    if (WSG) {
+        e = check_cuda(cudaMallocAsync((void **)&ws, sizeof(cx<T>) * size_t(grid) * (NR + 1) * p.fft, st),
+                       "cudaMallocAsync(workspace)");
+        if (e) return e;
+    }
+    kern<<<int(grid), kOT, smem, st>>>(p, m, (const cx<T> *)table, first_unit, (long long)n_units, idx,
+                                       (const T *)phi, (const T *)psi, (const cx<T> *)noise, idx_hat,
+                                       (cx<T> *)eq_out, ws, (unsigned long long *)counters);
+    count_launch();
+    e = check_cuda(cudaGetLastError(), "ofdm_tdl_kernel launch");
+    if (WSG) cudaFreeAsync(ws, st);
+    return e;
+}
+
+template <typename T, int NR, int NT>
+static int launch_typed(const OfdmP &p, const Modem &m, const void *table, uint64_t first_unit,
+                        int64_t n_units, const uint8_t *idx, const void *phi, const void *psi,
+                        const void *noise, uint8_t *idx_hat, void *eq_out, int64_t *counters,
+                        cudaStream_t st) {
+    int dev = 0, max_smem = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    size_t smem = ofdm_tdl_smem<T>(p, m.M, NR, NT, false);
+    const bool wsg = smem > size_t(max_smem);
+    if (wsg) {
+        smem = ofdm_tdl_smem<T>(p, m.M, NR, NT, true);
+        if (smem > size_t(max_smem)) {
+            set_error("OFDM/TDL frame needs %zu B of shared memory (> %d): fft/cp/taps too large", smem, max_smem);
+            return B200PHY_ERR_UNSUPPORTED;
+        }
+    }
+    const bool fused = !idx;
+#define B200_GO(F, W) launch_one<T, F, NR, NT, W>(p, m, table, first_unit, n_units, idx, phi, psi, noise, idx_hat, eq_out, counters, smem, st)
+    if (fused) return wsg ? B200_GO(true, true) : B200_GO(true, false);
+    return wsg ? B200_GO(false, true) : B200_GO(false, false);
+#undef B200_GO
+}
+
+template <>
+int launch_ofdm_tdl<B200_NR, B200_NT>(int dtype, const OfdmP &p, const Modem &m, const void *table,
+                                      uint64_t first_unit, int64_t n_units, const uint8_t *idx,
+                                      const void *phi, const void *psi, const void *noise,
+                                      uint8_t *idx_hat, void *eq_out, int64_t *counters,
+                                      cudaStream_t st) {
+    if (dtype == B200PHY_F32)
+        return launch_typed<float, B200_NR, B200_NT>(p, m, table, first_unit, n_units, idx, phi, psi, noise, idx_hat, eq_out, counters, st);
+    return launch_typed<double, B200_NR, B200_NT>(p, m, table, first_unit, n_units, idx, phi, psi, noise, idx_hat, eq_out, counters, st);
+}
+
+}  // namespace b200phy

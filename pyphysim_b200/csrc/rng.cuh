@@ -1,0 +1,73 @@
+// rng.cuh — the shared counter-based random stream (device side).
+// Contract (identical to oracle/philox.py):
+//   key     = (seed lo32, seed hi32)
+//   counter = (slot lo32, (stream << 16) | slot hi16, unit lo32, unit hi32),  slot = word / 4
+//   word w of (stream, unit) = lane w % 4 of that Philox4x32-10 block
+// Streams: 0 data symbols, 1 channel (Rayleigh H / Jakes phases), 2 noise.
+#pragma once
+#include "common.cuh"
+
+namespace b200phy {
+
+enum { STREAM_DATA = 0, STREAM_CHANNEL = 1, STREAM_NOISE = 2 };
+
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += 0x9E3779B9u;
+        k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+
+__device__ __forceinline__ uint4 rng_block(uint64_t seed, uint32_t stream, uint64_t unit, uint64_t slot) {
+    const uint4 c = make_uint4(uint32_t(slot), (stream << 16) | (uint32_t(slot >> 32) & 0xffffu),
+                               uint32_t(unit), uint32_t(unit >> 32));
+    return philox4x32_10(c, make_uint2(uint32_t(seed), uint32_t(seed >> 32)));
+}
+
+__device__ __forceinline__ uint32_t lane_of(const uint4 &b, int l) {
+    return l == 0 ? b.x : (l == 1 ? b.y : (l == 2 ? b.z : b.w));
+}
+
+// u(x) = (x + 0.5) * 2^-32.  f32: float(x) * 2^-32 + 2^-33 (the multiply is exact, so the fused and
+// unfused forms round identically and the host float32 evaluation is bit-identical).
+template <typename T> __device__ __forceinline__ T uniform01(uint32_t x);
+template <> __device__ __forceinline__ float uniform01<float>(uint32_t x) {
+    return __fmaf_rn(__uint2float_rn(x), 0x1p-32f, 0x1p-33f);
+}
+template <> __device__ __forceinline__ double uniform01<double>(uint32_t x) {
+    return (double(x) + 0.5) * 0x1p-32;
+}
+
+__device__ __forceinline__ void sincos2pi(float u, float *s, float *c) { sincospif(2.0f * u, s, c); }
+__device__ __forceinline__ void sincos2pi(double u, double *s, double *c) { sincospi(2.0 * u, s, c); }
+
+// complex normal with E|c|^2 = 1 (randn_c, util/misc.py:327-355) by Box-Muller on two words
+template <typename T> __device__ __forceinline__ cx<T> cnormal(uint32_t w0, uint32_t w1) {
+    const T rad = sqrt(-log(uniform01<T>(w0)));
+    T s, c;
+    sincos2pi(uniform01<T>(w1), &s, &c);
+    return {rad * c, rad * s};
+}
+
+// complex normal number j of (stream, unit): words (2j, 2j+1)
+template <typename T>
+__device__ __forceinline__ cx<T> cnormal_at(uint64_t seed, uint32_t stream, uint64_t unit, uint64_t j) {
+    const uint4 b = rng_block(seed, stream, unit, j >> 1);
+    return (j & 1) ? cnormal<T>(b.z, b.w) : cnormal<T>(b.x, b.y);
+}
+
+// Jakes phase: 2*pi*u (channels/fading_generators.py:413-414); single rounded multiply
+template <typename T> __device__ __forceinline__ T phase_from_word(uint32_t x);
+template <> __device__ __forceinline__ float phase_from_word<float>(uint32_t x) {
+    return __fmul_rn(6.283185307179586f, uniform01<float>(x));
+}
+template <> __device__ __forceinline__ double phase_from_word<double>(uint32_t x) {
+    return __dmul_rn(6.283185307179586, uniform01<double>(x));
+}
+
+}  // namespace b200phy

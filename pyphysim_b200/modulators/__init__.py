@@ -1,0 +1,4 @@
+"""Mirror of pyphysim.modulators: digital modulators and OFDM."""
+from .fundamental import BPSK, PSK, QAM, QPSK, Modulator  # noqa: F401
+
+__all__ = ['Modulator', 'PSK', 'QPSK', 'BPSK', 'QAM']

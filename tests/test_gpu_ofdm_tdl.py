@@ -1,0 +1,191 @@
+"""GPU parity of the fused OFDM-over-Jakes/TDL link (configs C3, C5 and the 2x2 headline workload)
+against the oracle and the golden fixtures made from the unmodified reference."""
+import numpy as np
+import pytest
+
+from oracle import fading
+from oracle import links as OL
+from oracle import modulators as md
+
+from gpu_util import (assert_decisions, assert_samples_close, cuda, oracle_modem, product_modem)
+
+pytestmark = pytest.mark.gpu
+SEED = 0xC0FFEE
+
+
+def _t(x):
+    return x.cpu().numpy()
+
+
+def make_pair(kind, M, fft, cp, used, n_sym=1, Nr=1, Nt=1, profile=fading.COST259_TU, Fd=10.0, L=20,
+              snr_dB=20.0, fnv=None, dtype='f64', jakes='auto', Ts=None, t0=None):
+    """(oracle config, product link) describing the same link."""
+    from pyphysim_b200 import links
+    om = oracle_modem(kind, M)
+    nv = 1 / md.dB2Linear(snr_dB)
+    cfg = OL.OfdmTdlConfig(om, fft, cp, used, n_sym=n_sym, Nr=Nr, Nt=Nt, profile=profile, Fd=Fd, L=L,
+                           noise_var=nv, filter_noise_var=fnv, Ts=Ts, t0=t0)
+    link = links.OfdmTdlLink(product_modem(kind, M), fft, cp, used, num_ofdm_symbols=n_sym, Nr=Nr, Nt=Nt,
+                             tap_powers_linear=cfg.tap_powers, tap_delays=cfg.delays, Fd=Fd, Ts=cfg.Ts,
+                             L=L, t0=cfg.t0, noise_var=nv, filter_noise_var=fnv, dtype=dtype,
+                             jakes_mode=jakes, seed=SEED)
+    return cfg, link
+
+
+def run_stream_vs_oracle(cfg, link, units, exact, rel, eps=2e-4):
+    """Host Philox draws -> (oracle, device stream mode); compare equalised samples and indices."""
+    npdt = np.float64 if link.dtype == 1 else np.float32
+    idx, phi, psi, noise = OL.draws_ofdm_tdl(cfg, SEED, units, dtype=npdt)
+    n = len(units)
+    draws = (cuda(idx.astype(np.uint8)), cuda(phi.reshape(n, -1)), cuda(psi.reshape(n, -1)), cuda(noise))
+    cnt, hat, eq = link.run(n, first_unit=int(units[0]), draws=draws, want_idx=True, want_eq=True)
+    ref_hat = np.empty_like(idx)
+    ref_eq = np.empty(idx.shape, dtype=complex)
+    for u in range(n):
+        ref_hat[u], det = OL.ofdm_tdl_frame(cfg, idx[u], phi[u].astype(np.float64), psi[u].astype(np.float64),
+                                            noise[u].astype(np.complex128), detail=True)
+        ref_eq[u] = det['eq']
+    assert_samples_close(_t(eq), ref_eq, rel, 'equalised symbols')
+    nbad = assert_decisions(_t(hat), ref_hat, cfg.modem, ref_eq, exact=exact, eps=eps)
+    ref_cnt = OL.counters(idx, ref_hat, cfg.modem.bits)
+    assert abs(int(cnt[0]) - int(ref_cnt[0])) <= nbad and abs(int(cnt[1]) - int(ref_cnt[1])) <= 8 * nbad
+    assert cnt[2] == ref_cnt[2] and cnt[3] == ref_cnt[3]
+    return cnt, ref_cnt
+
+
+# ------------------------------------------------------------------ draws
+def test_ofdm_draws_match_host_philox():
+    cfg, link = make_pair('qam', 64, 128, 16, 100, n_sym=2, Nr=2, Nt=2, dtype='f64')
+    idx, phi, psi, noise = link.draw(40, 3)
+    hi, hphi, hpsi, hn = OL.draws_ofdm_tdl(cfg, SEED, np.arange(40, 43))
+    assert np.array_equal(_t(idx), hi)
+    assert np.array_equal(_t(phi), hphi.reshape(3, -1))            # phases: bit exact
+    assert np.array_equal(_t(psi), hpsi.reshape(3, -1))
+    np.testing.assert_allclose(_t(noise), hn, atol=1e-13)
+    cfg, link = make_pair('qam', 64, 128, 16, 100, dtype='f32')
+    idx, phi, psi, noise = link.draw(0, 2)
+    hi, hphi, hpsi, hn = OL.draws_ofdm_tdl(cfg, SEED, np.arange(2), dtype=np.float32)
+    assert np.array_equal(_t(phi), hphi.reshape(2, -1)) and np.array_equal(_t(psi), hpsi.reshape(2, -1))
+    np.testing.assert_allclose(_t(noise), hn, atol=2e-6)
+
+
+# ------------------------------------------------------------------ golden fixtures (reference output)
+def test_c3_golden_full_size(golden):
+    g = golden('links')
+    for jakes in ('recurrence', 'auto'):
+        cfg, link = make_pair('qam', 64, 1024, 72, 1024, dtype='f64', jakes=jakes)
+        idx, phi, psi, noise = OL.draws_ofdm_tdl(cfg, SEED, g['c3_units'])
+        draws = (cuda(idx.astype(np.uint8)), cuda(phi.reshape(2, -1)), cuda(psi.reshape(2, -1)), cuda(noise))
+        cnt, hat, eq = link.run(2, draws=draws, want_idx=True, want_eq=True)
+        assert_samples_close(_t(eq), g['c3_eq'], 1e-9, 'C3 vs reference (%s)' % jakes)
+        assert np.array_equal(_t(hat), g['c3_hat'])
+        assert np.array_equal(cnt, OL.counters(idx, g['c3_hat'], 6)) and cnt[0] > 0
+
+
+def test_mimo2x2_golden(golden):
+    g = golden('links')
+    cfg, link = make_pair('qam', 16, 256, 18, 200, n_sym=2, Nr=2, Nt=2, Fd=300.0, snr_dB=25.0,
+                          dtype='f64', jakes='recurrence')
+    idx, phi, psi, noise = OL.draws_ofdm_tdl(cfg, SEED, g['m2_units'])
+    draws = (cuda(idx.astype(np.uint8)), cuda(phi.reshape(2, -1)), cuda(psi.reshape(2, -1)), cuda(noise))
+    cnt, hat, eq = link.run(2, first_unit=10, draws=draws, want_idx=True, want_eq=True)
+    assert_samples_close(_t(eq), g['m2_eq'], 1e-8, '2x2 vs reference')
+    assert np.array_equal(_t(hat), g['m2_hat'])
+
+
+# ------------------------------------------------------------------ oracle parity, f64
+@pytest.mark.parametrize('jakes', ['recurrence', 'poly'])
+def test_c3_f64(jakes):
+    Fd = 10.0 if jakes == 'recurrence' else 2.0
+    cfg, link = make_pair('qam', 64, 1024, 72, 1024, dtype='f64', jakes=jakes, Fd=Fd)
+    run_stream_vs_oracle(cfg, link, np.arange(100, 104), exact=True, rel=1e-9)
+
+
+@pytest.mark.parametrize('case', [
+    dict(kind='qam', M=16, fft=64, cp=16, used=52, n_sym=3, Fd=500.0, profile=fading.COST259_RA, Ts=2e-7),
+    dict(kind='psk', M=8, fft=128, cp=0, used=60, n_sym=2, Fd=50.0, Ts=1e-7),
+    dict(kind='bpsk', M=2, fft=256, cp=32, used=256, n_sym=1, Fd=1000.0, L=8, Ts=1e-7),
+    dict(kind='qam', M=256, fft=2048, cp=144, used=1200, n_sym=1, Fd=10.0),
+    dict(kind='qam', M=64, fft=512, cp=52, used=300, n_sym=2, Fd=5.0, Ts=2.0e-7, L=33),
+    dict(kind='qam', M=16, fft=256, cp=200, used=100, n_sym=2, Fd=100.0, profile=fading.COST259_HT, Ts=1e-7),
+])
+def test_siso_shapes_f64(case):
+    cfg, link = make_pair(dtype='f64', **case)
+    run_stream_vs_oracle(cfg, link, np.arange(2), exact=True, rel=1e-9)
+
+
+@pytest.mark.parametrize('case', [
+    dict(kind='qam', M=64, fft=1024, cp=72, used=1024, Nr=2, Nt=2, snr_dB=25.0),           # headline workload
+    dict(kind='qam', M=16, fft=128, cp=16, used=100, n_sym=2, Nr=2, Nt=2, Fd=400.0, fnv=0.0, Ts=1e-7),  # ZF
+    dict(kind='qam', M=16, fft=128, cp=16, used=100, n_sym=2, Nr=2, Nt=1, Fd=400.0, Ts=1e-7),
+    dict(kind='qam', M=16, fft=256, cp=18, used=200, Nr=4, Nt=2, snr_dB=15.0),
+    dict(kind='qam', M=256, fft=2048, cp=144, used=2048, Nr=4, Nt=4, snr_dB=30.0),          # C5
+])
+def test_mimo_shapes_f64(case):
+    cfg, link = make_pair(dtype='f64', **case)
+    # the normal-equation solve in double vs LAPACK pinv/solve: 1e-7 at ill-conditioned subcarriers
+    run_stream_vs_oracle(cfg, link, np.arange(7, 9), exact=False, rel=1e-7, eps=1e-6)
+
+
+# ------------------------------------------------------------------ f32 (throughput arithmetic)
+@pytest.mark.parametrize('case,jakes', [
+    (dict(kind='qam', M=64, fft=1024, cp=72, used=1024), 'auto'),
+    (dict(kind='qam', M=64, fft=1024, cp=72, used=1024), 'recurrence'),
+    (dict(kind='qam', M=64, fft=1024, cp=72, used=1024, Nr=2, Nt=2, snr_dB=25.0), 'auto'),
+    (dict(kind='qam', M=256, fft=2048, cp=144, used=2048, Nr=4, Nt=4, snr_dB=30.0), 'auto'),
+    (dict(kind='qam', M=16, fft=128, cp=16, used=100, n_sym=3, Fd=800.0, Ts=1e-7), 'auto'),
+])
+def test_f32_within_tolerance(case, jakes):
+    cfg, link = make_pair(dtype='f32', jakes=jakes, **case)
+    # 1e-5 relative on samples (BASELINE north_star); MIMO detection amplifies by ||G|| <= 1/(2 sigma)
+    rel = 1e-5 if cfg.Nt == 1 else 1e-4
+    run_stream_vs_oracle(cfg, link, np.arange(50, 53), exact=False, rel=rel, eps=2e-3)
+
+
+# ------------------------------------------------------------------ fused mode, sharding, properties
+@pytest.mark.parametrize('dtype', ['f32', 'f64'])
+@pytest.mark.parametrize('ant', [(1, 1), (2, 2)])
+def test_fused_equals_stream_on_device_draws(dtype, ant):
+    import torch
+    cfg, link = make_pair('qam', 64, 256, 18, 200, n_sym=2, Nr=ant[0], Nt=ant[1], dtype=dtype, Fd=200.0)
+    n = 37
+    draws = link.draw(1000, n)
+    c_s, hat_s = link.run(n, first_unit=1000, draws=draws, want_idx=True)
+    c_f, hat_f = link.run(n, first_unit=1000, want_idx=True)
+    assert np.array_equal(c_s, c_f) and torch.equal(hat_s, hat_f)
+    acc = torch.zeros(4, dtype=torch.int64, device='cuda')
+    for a, b in ((0, 5), (5, 6), (6, n)):
+        link.run(b - a, first_unit=1000 + a, counters=acc)
+    assert np.array_equal(_t(acc), c_f)                      # invariant to batch split / GPU sharding
+    c_h, hat_h = link.run_host(n, first_unit=1000, draws=tuple(t.cpu().pin_memory() for t in draws),
+                               want_idx=True)
+    assert np.array_equal(c_h, c_f) and np.array_equal(hat_h.numpy(), _t(hat_f))
+
+
+def test_full_size_properties():
+    """At BASELINE sizes: noiseless frames decode without error; error rate grows with noise;
+    repeatable; totals exact."""
+    cfg, link = make_pair('qam', 64, 1024, 72, 1024, Nr=2, Nt=2, dtype='f32', snr_dB=25.0)
+    n = 2000
+    link.set_noise_var(0.0, filter_noise_var=1e-6)
+    c0 = link.run(n)
+    assert c0[2] == n * 2048 and c0[3] == 6 * c0[2] and c0[0] <= 1e-5 * c0[2]
+    sers = []
+    for snr in (30.0, 20.0, 10.0):
+        link.set_noise_var(1 / md.dB2Linear(snr))
+        c = link.run(n)
+        assert np.array_equal(c, link.run(n))                # deterministic
+        sers.append(c[0] / c[2])
+    assert sers[0] < sers[1] < sers[2] and sers[2] > 0.3
+
+
+def test_unsupported_shapes_raise():
+    from pyphysim_b200 import links
+    pm = product_modem('qam', 16)
+    with pytest.raises(NotImplementedError):
+        links.OfdmTdlLink(pm, 64, 16, 52, Nr=3, Nt=3, tap_powers_linear=[1.0], tap_delays=[0]).run(1)
+    with pytest.raises(ValueError):
+        links.OfdmTdlLink(pm, 64, 16, 53, tap_powers_linear=[1.0], tap_delays=[0]).run(1)
+    with pytest.raises(NotImplementedError):
+        links.OfdmTdlLink(pm, 64, 16, 52, tap_powers_linear=[1.0], tap_delays=[0], Fd=1e5, Ts=1e-4,
+                          jakes_mode='poly').run(1)
