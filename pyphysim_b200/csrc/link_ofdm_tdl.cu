@@ -6,13 +6,15 @@
 
 namespace b200phy {
 
-// Error model of the POLY mode.  Within a segment the kernel evaluates the 3rd-order Taylor
-// polynomial of exp(j w dt) around the segment centre for |dt| <= seg/2 + mem samples; the
-// remainder of each unit ray is (w dt)^4/24 and a tap sums L rays of amplitude sqrt(P_l/L),
-// so |error| <= sqrt(L P_l) x^4/24 <= sqrt(L) x^4/24 with x = 2 pi Fd Ts (seg/2 + mem).
-static double poly_error_bound(const b200phy_ofdm_tdl_params *q, int seg_len, int mem) {
-    const double x = 2.0 * M_PI * fabs(q->Fd) * q->Ts * 1.0000000001 * (0.5 * seg_len + mem);
-    return sqrt(double(q->L)) * x * x * x * x / 24.0;
+// Error model of the POLY mode.  Around the expansion point the kernel evaluates the order-P Taylor
+// polynomial of exp(j w tau) for |tau| <= tau_max samples; the remainder of each unit ray is
+// (w tau)^(P+1)/(P+1)! and a tap sums L rays of amplitude sqrt(P_l/L), so
+// |error| <= sqrt(L P_l) x^(P+1)/(P+1)! <= sqrt(L) x^(P+1)/(P+1)!  with x = 2 pi Fd Ts tau_max.
+static double poly_error_bound(const b200phy_ofdm_tdl_params *q, int order, double tau_max) {
+    const double x = 2.0 * M_PI * fabs(q->Fd) * q->Ts * 1.0000000001 * tau_max;
+    double r = sqrt(double(q->L));
+    for (int i = 1; i <= order + 1; ++i) r *= x / i;
+    return r;
 }
 
 static int fill_params(const b200phy_ofdm_tdl_params *q, const Modem &m, OfdmP *out) {
@@ -68,15 +70,38 @@ static int fill_params(const b200phy_ofdm_tdl_params *q, const Modem &m, OfdmP *
     const double tol = q->dtype == B200PHY_F32 ? 2e-8 : 2e-14;
     int seg = q->fft;
     const int min_seg = q->fft < kOT ? q->fft : kOT;
-    while (seg > min_seg && poly_error_bound(q, seg, p.mem) > tol) seg >>= 1;
-    const bool poly_ok = poly_error_bound(q, seg, p.mem) <= tol;
+    while (seg > min_seg && poly_error_bound(q, 3, 0.5 * seg) > tol) seg >>= 1;
+    const bool poly_ok = poly_error_bound(q, 3, 0.5 * seg) <= tol;
     if (q->jakes_mode == B200PHY_JAKES_POLY && !poly_ok) {
         set_error("JAKES_POLY requested but its error bound %.3g exceeds %.3g (Fd*Ts too large)",
-                  poly_error_bound(q, seg, p.mem), tol);
+                  poly_error_bound(q, 3, 0.5 * seg), tol);
         return B200PHY_ERR_UNSUPPORTED;
     }
     p.poly = (q->jakes_mode == B200PHY_JAKES_POLY) || (q->jakes_mode == B200PHY_JAKES_AUTO && poly_ok);
     p.seg_len = seg; p.seg_lg = ilog2(seg); p.nseg = q->fft / seg;
+    p.porder = poly_error_bound(q, 2, 0.5 * seg) <= tol ? 2 : 3;
+    p.gbar_poly = 0;
+    if (p.poly && p.nseg == 1) {
+        // the symbol-mean taps (CP included) from the same polynomial, extrapolated over CP / delay
+        const double tg = 0.5 * q->fft + (q->cp > p.mem ? q->cp : p.mem);
+        if (poly_error_bound(q, p.porder, tg) <= tol) p.gbar_poly = 1;
+        else if (poly_error_bound(q, 3, tg) <= tol) { p.porder = 3; p.gbar_poly = 1; }
+    }
+    for (int l = 0; l < q->n_taps; ++l) {
+        double m1 = 0, m2 = 0, m3 = 0;
+        const double c = q->cp + 0.5 * (q->fft - 1) - q->delays[l];
+        for (int n = 0; n < p.S; ++n) { const double t = n - c; m1 += t; m2 += t * t; m3 += t * t * t; }
+        p.mu[0][l] = m1 / p.S; p.mu[1][l] = m2 / p.S; p.mu[2][l] = m3 / p.S;
+    }
+    // float cos(phi) perturbs every ray frequency by ~1e-7 relative: harmless while the total phase
+    // advance w0 * t_end stays small
+    p.cos_f32 = (q->dtype == B200PHY_F32) && (p.w0 * (fabs(q->t0) + p.N * p.Ts1) < 0.05);
+    {
+        const int items = q->n_taps * q->Nr;
+        int g = 1;
+        while (g < 16 && (g * 2) * items <= kOT) g *= 2;
+        p.cgrp = g;
+    }
     if (q->jakes_mode != B200PHY_JAKES_AUTO && q->jakes_mode != B200PHY_JAKES_POLY &&
         q->jakes_mode != B200PHY_JAKES_RECURRENCE) { set_error("bad jakes_mode"); return B200PHY_ERR_INVALID; }
     (void)m;

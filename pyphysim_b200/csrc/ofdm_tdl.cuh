@@ -11,9 +11,10 @@
 // Jakes taps h(n) = L^-1/2 sum_o exp(j(theta_o + n*Delta_o)) (fading_generators.py:519-523) are
 // evaluated one of two ways (DESIGN.md "Jakes evaluation"):
 //   RECURRENCE  chunks of 8 samples: exact sincos at the chunk start, then z += z*d rotations.
-//   POLY        3rd-order Taylor polynomial in the sample offset around a segment centre, used when
-//               sqrt(L)*(w*dmax)^4/24 is below the dtype's resolution (slow fading: all BASELINE
-//               configs); 4 FMAs per tap sample instead of 6*L.
+//   POLY        2nd/3rd-order Taylor polynomial in the output-sample offset tau around a segment
+//               centre (per tap the expansion point is shifted by its delay so tau is common to all
+//               taps), used when sqrt(L)*(w*tau_max)^(P+1)/(P+1)! is below the dtype's resolution
+//               (slow fading: all BASELINE configs); 4-6 FMAs per tap sample instead of 6*L.
 #pragma once
 #include "common.cuh"
 #include "linalg.cuh"
@@ -28,11 +29,16 @@ constexpr int kCH = 8;         // recurrence chunk length
 struct OfdmP {
     int fft, lg, cp, used, half, n_sym, S, N, mem, n_taps, L, n_data;
     int poly, nseg, seg_len, seg_lg;
+    int porder;     // Taylor order of the POLY mode (2 or 3)
+    int gbar_poly;  // 1: symbol-mean taps from the polynomial moments mu (nseg == 1 only)
+    int cos_f32;    // 1: cos(phi) may be evaluated in float (total phase advance is small)
+    int cgrp;       // lanes cooperating on one (tap, rx) item in the oscillator setup (power of 2)
     int row;        // noise normals per rx row in the Philox layout: 2*ceil((N+mem)/2)
     int P, P4;      // phases per frame, rounded up to a multiple of 4
     int ifft_in_w;  // 1: scatter into W so that the ping-pong IFFT ends in E.body
     int delays[B200PHY_MAX_TAPS];
     double amp[B200PHY_MAX_TAPS];   // sqrt(P_l / L)
+    double mu[3][B200PHY_MAX_TAPS]; // mean of tau^p (p = 1..3) over the S samples of a symbol, per tap
     double w0;      // 2*pi*Fd
     double Ts1;     // Ts * 1.0000000001 (fading_generators.py:462)
     double t0;
@@ -57,7 +63,7 @@ __device__ cx<T> *fft_stockham(cx<T> *a, cx<T> *b, const cx<T> *tw, int N, int l
             const int k = j & (Ns - 1);
             cx<T> v0 = src[j], v1 = src[j + q], v2 = src[j + 2 * q], v3 = src[j + 3 * q];
             if (Ns > 1) {
-                const int ts = k * (q / Ns);
+                const int ts = k << (lg - 2 - 2 * st);          // k * (N/4) / Ns
                 cx<T> w1 = tw[ts], w2 = tw[2 * ts], w3 = tw[3 * ts];
                 if (INV) { w1.im = -w1.im; w2.im = -w2.im; w3.im = -w3.im; }
                 v1 = v1 * w1; v2 = v2 * w2; v3 = v3 * w3;
@@ -79,7 +85,7 @@ __device__ cx<T> *fft_stockham(cx<T> *a, cx<T> *b, const cx<T> *tw, int N, int l
         const int h = N >> 1;
         for (int j = threadIdx.x; j < h; j += blockDim.x) {
             const int k = j & (Ns - 1);
-            cx<T> w = tw[k * (h / Ns)];
+            cx<T> w = tw[k];                                     // last pass: Ns == N/2
             if (INV) w.im = -w.im;
             const cx<T> v0 = src[j], v1 = src[j + h] * w;
             const int j0 = ((j - k) << 1) + k;
@@ -115,6 +121,17 @@ __device__ __forceinline__ double reduce_2pi(double th) {
 __device__ __forceinline__ void sincos_t(float x, float *s, float *c) { sincosf(x, s, c); }
 __device__ __forceinline__ void sincos_t(double x, double *s, double *c) { sincos(x, s, c); }
 
+// read-once stream data: 8/16-byte loads through the read-only path
+template <typename T> __device__ __forceinline__ cx<T> load_stream(const cx<T> *p) {
+    if constexpr (sizeof(T) == 4) {
+        const float2 v = __ldg(reinterpret_cast<const float2 *>(p));
+        return {v.x, v.y};
+    } else {
+        const double2 v = __ldg(reinterpret_cast<const double2 *>(p));
+        return {v.x, v.y};
+    }
+}
+
 template <typename P, int N> __device__ __forceinline__ P pick(P const (&arr)[N], int r) {
     P v = arr[0];
 #pragma unroll
@@ -137,6 +154,47 @@ template <typename T> __device__ __forceinline__ T dirichlet(double dl, int S) {
 }
 
 // ================================================================= the kernel
+// Horner evaluation of the tap polynomial at tau and accumulation of g*x, P = 2 or 3
+template <typename T, int P>
+__device__ __forceinline__ void tap_mac(cx<T> &acc, const cx<T> (&cf)[4], T tau, cx<T> x) {
+    cx<T> g;
+    if (P == 3) {
+        g.re = fma(cf[3].re, tau, cf[2].re);
+        g.im = fma(cf[3].im, tau, cf[2].im);
+        g.re = fma(g.re, tau, cf[1].re);
+        g.im = fma(g.im, tau, cf[1].im);
+    } else {
+        g.re = fma(cf[2].re, tau, cf[1].re);
+        g.im = fma(cf[2].im, tau, cf[1].im);
+    }
+    g.re = fma(g.re, tau, cf[0].re);
+    g.im = fma(g.im, tau, cf[0].im);
+    cmac(acc, g, x);
+}
+
+// acc += (-j)^E * v for a compile-time E
+template <typename T, int E> __device__ __forceinline__ void add_rot(cx<T> &acc, cx<T> v) {
+    if ((E & 3) == 0) { acc.re += v.re; acc.im += v.im; }
+    else if ((E & 3) == 1) { acc.re += v.im; acc.im -= v.re; }
+    else if ((E & 3) == 2) { acc.re -= v.re; acc.im -= v.im; }
+    else { acc.re -= v.im; acc.im += v.re; }
+}
+
+// H[u] += (-j)^(u D) * gbar_l[r][t] * w for the four bins k0 + u fft/4 (D = tap delay mod 4)
+template <typename T, int NR, int NT, int D>
+__device__ __forceinline__ void hk_accum4(cx<T> (&H)[4][NR][NT], const cx<T> *__restrict__ gl, cx<T> w) {
+#pragma unroll
+    for (int r = 0; r < NR; ++r)
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+            const cx<T> pr = gl[r * NT + t] * w;
+            add_rot<T, 0>(H[0][r][t], pr);
+            add_rot<T, D>(H[1][r][t], pr);
+            add_rot<T, 2 * D>(H[2][r][t], pr);
+            add_rot<T, 3 * D>(H[3][r][t], pr);
+        }
+}
+
 template <typename T, bool FUSED, int NR, int NT, bool WSG>
 __global__ void __launch_bounds__(kOT, (sizeof(T) == 4 && NR * NT <= 4) ? 3 : 1)
 ofdm_tdl_kernel(const __grid_constant__ OfdmP p, const Modem m, const cx<T> *__restrict__ tab_g,
@@ -145,10 +203,10 @@ ofdm_tdl_kernel(const __grid_constant__ OfdmP p, const Modem m, const cx<T> *__r
                 const cx<T> *__restrict__ noise_g, uint8_t *__restrict__ idx_hat,
                 cx<T> *__restrict__ eq_out, cx<T> *__restrict__ ws_g, unsigned long long *counters) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x;
     const int fft = p.fft, S = p.S, mem = p.mem, cp = p.cp;
 
-    // ---- carve shared memory
+    // ---- carve shared memory (mirrored by ofdm_tdl_smem below)
     unsigned char *sp = smem_raw;
     auto take = [&](size_t bytes) { unsigned char *r = sp; sp += (bytes + 15) & ~size_t(15); return r; };
     cx<T> *tw = (cx<T> *)take(sizeof(cx<T>) * fft);
@@ -176,6 +234,7 @@ ofdm_tdl_kernel(const __grid_constant__ OfdmP p, const Modem m, const cx<T> *__r
     unsigned sym_err = 0, bit_err = 0;
     const T sigma = T(p.sigma), tx_scale = T(p.tx_scale), rx_scale = T(p.rx_scale);
     const int n_items = p.n_taps * NR;
+    const int G = p.cgrp, sub = tid & (G - 1);
 
     for (long long frame = blockIdx.x; frame < n_units; frame += gridDim.x) {
         const uint64_t unit = first_unit + uint64_t(frame);
@@ -201,7 +260,13 @@ ofdm_tdl_kernel(const __grid_constant__ OfdmP p, const Modem m, const cx<T> *__r
                     }
                 } else {
                     const uint8_t *src = idx_g + frame * p.n_data + w0;
-                    for (int i = tid; i < cnt; i += kOT) dsym[i] = src[i];
+                    if ((cnt & 3) == 0 && ((frame * p.n_data + w0) & 3) == 0) {
+                        const uint32_t *s4 = reinterpret_cast<const uint32_t *>(src);
+                        uint32_t *d4 = reinterpret_cast<uint32_t *>(dsym);
+                        for (int i = tid; i < (cnt >> 2); i += kOT) d4[i] = __ldg(s4 + i);
+                    } else {
+                        for (int i = tid; i < cnt; i += kOT) dsym[i] = src[i];
+                    }
                 }
                 const int m0 = n_s + cp;          // first needed rx sample of this symbol
                 if constexpr (FUSED) {
@@ -219,7 +284,7 @@ ofdm_tdl_kernel(const __grid_constant__ OfdmP p, const Modem m, const cx<T> *__r
 #pragma unroll
                     for (int r = 0; r < NR; ++r) {
                         const cx<T> *src = noise_g + (size_t(frame) * NR + r) * rowlen + m0;
-                        for (int j = tid; j < fft; j += kOT) Yp[r][j] = sigma * src[j];
+                        for (int j = tid; j < fft; j += kOT) Yp[r][j] = sigma * load_stream(src + j);
                     }
                 }
             }
@@ -235,39 +300,53 @@ ofdm_tdl_kernel(const __grid_constant__ OfdmP p, const Modem m, const cx<T> *__r
                     if (q >= 0) v = tx_scale * map_symbol<T>(m, tab, dsym[q * NT + t]);
                     in[k] = v;
                 }
-                // ---------------- C: per-oscillator setup for tx antenna t (lanes = rays)
-                for (int it = warp; it < n_items; it += kOT / 32) {
-                    const int l = it / NR, r = it % NR;
-                    const T amp = T(p.amp[l]);
-                    cx<T> gsum = {T(0), T(0)};
-                    cx<T> a[4][4];      // [seg][order]; nseg <= 4 handled in registers per pass
-                    for (int sg0 = 0; sg0 < (p.poly ? p.nseg : 1); sg0 += 4) {
-#pragma unroll
-                        for (int u = 0; u < 4; ++u)
-#pragma unroll
-                            for (int o = 0; o < 4; ++o) a[u][o] = {T(0), T(0)};
-                        for (int o = lane; o < p.L; o += 32) {
-                            const int i = ((o * p.n_taps + l) * NR + r) * NT + t;
-                            T phi, psi;
-                            if constexpr (FUSED) {
-                                phi = phase_from_word<T>(lane_of(rng_block(p.seed, STREAM_CHANNEL, unit, uint64_t(i >> 2)), i & 3));
-                                const int i2 = p.P4 + i;
-                                psi = phase_from_word<T>(lane_of(rng_block(p.seed, STREAM_CHANNEL, unit, uint64_t(i2 >> 2)), i2 & 3));
-                            } else {
-                                phi = phi_g[size_t(frame) * p.P + i];
-                                psi = psi_g[size_t(frame) * p.P + i];
-                            }
-                            const double cphi = cos(double(phi));
-                            const double dl = p.w0 * p.Ts1 * cphi;             // phase step per sample
-                            const double th0 = double(psi) + p.w0 * cphi * p.t0;
-                            if (sg0 == 0) {
-                                // mean tap over the S samples of this symbol (CP included, ofdm.py:541-548)
-                                const double mid = reduce_2pi(fma(dl, double(n_s) + 0.5 * double(S - 1), th0));
-                                T sn, cs;
-                                sincos_t(T(mid), &sn, &cs);
-                                const T g = amp * dirichlet<T>(dl, S);
-                                gsum.re += g * cs;
-                                gsum.im += g * sn;
+                // ---------------- C: per-ray setup for tx antenna t.  G lanes share one (tap, rx) item,
+                // each summing a subset of the L rays; a G-wide shuffle reduction finishes the item.
+                for (int sg = 0; sg < (p.poly ? p.nseg : 1); ++sg) {
+                    for (int it0 = 0; it0 < n_items; it0 += kOT / G) {
+                        const int it = it0 + tid / G;
+                        const bool act = it < n_items;
+                        const int l = act ? it / NR : 0, r = act ? it % NR : 0;
+                        const T amp = T(p.amp[l]);
+                        cx<T> a0 = {T(0), T(0)}, a1 = a0, a2 = a0, a3 = a0, gs = a0;
+                        const double cseg = double(n_s + cp + sg * p.seg_len - p.delays[l]) + 0.5 * double(p.seg_len - 1);
+                        if (act)
+                            for (int o = sub; o < p.L; o += G) {
+                                const int i = ((o * p.n_taps + l) * NR + r) * NT + t;
+                                T phi, psi;
+                                if constexpr (FUSED) {
+                                    phi = phase_from_word<T>(lane_of(rng_block(p.seed, STREAM_CHANNEL, unit, uint64_t(i >> 2)), i & 3));
+                                    const int i2 = p.P4 + i;
+                                    psi = phase_from_word<T>(lane_of(rng_block(p.seed, STREAM_CHANNEL, unit, uint64_t(i2 >> 2)), i2 & 3));
+                                } else {
+                                    phi = __ldg(phi_g + size_t(frame) * p.P + i);
+                                    psi = __ldg(psi_g + size_t(frame) * p.P + i);
+                                }
+                                const double cphi = (sizeof(T) == 4 && p.cos_f32) ? double(cosf(float(phi))) : cos(double(phi));
+                                const double dl = p.w0 * p.Ts1 * cphi;             // phase step per sample
+                                const double th0 = fma(p.w0 * cphi, p.t0, double(psi));
+                                if (p.poly) {
+                                    T sn, cs;
+                                    sincos_t(T(reduce_2pi(fma(dl, cseg, th0))), &sn, &cs);
+                                    const cx<T> e = {amp * cs, amp * sn};
+                                    const T d1 = T(dl), d2 = T(-0.5 * dl * dl);
+                                    a0.re += e.re;        a0.im += e.im;
+                                    a1.re -= d1 * e.im;   a1.im += d1 * e.re;     // (j dl) e
+                                    a2.re += d2 * e.re;   a2.im += d2 * e.im;     // -(dl^2/2) e
+                                    if (p.porder == 3) {
+                                        const T d3 = T(dl * dl * dl * (1.0 / 6.0));
+                                        a3.re += d3 * e.im;   a3.im -= d3 * e.re; // -j(dl^3/6) e
+                                    }
+                                }
+                                if (sg == 0 && !p.gbar_poly) {
+                                    // mean tap over the S samples of this symbol (CP included, ofdm.py:541-548)
+                                    const double mid = reduce_2pi(fma(dl, double(n_s) + 0.5 * double(S - 1), th0));
+                                    T sn, cs;
+                                    sincos_t(T(mid), &sn, &cs);
+                                    const T g = amp * dirichlet<T>(dl, S);
+                                    gs.re += g * cs;
+                                    gs.im += g * sn;
+                                }
                                 if (!p.poly) {
                                     OscRec<T> rec;
                                     rec.th0 = th0; rec.dl = dl;
@@ -278,37 +357,30 @@ ofdm_tdl_kernel(const __grid_constant__ OfdmP p, const Modem m, const cx<T> *__r
                                     osc[(l * NR + r) * p.L + o] = rec;
                                 }
                             }
+                        for (int o = G >> 1; o > 0; o >>= 1) {
                             if (p.poly) {
-                                const T d1 = T(dl), d2 = T(-0.5 * dl * dl), d3 = T(dl * dl * dl * (1.0 / 6.0));
-#pragma unroll
-                                for (int u = 0; u < 4; ++u)
-                                    if (sg0 + u < p.nseg) {
-                                        const double c = double(n_s + cp + (sg0 + u) * p.seg_len) + 0.5 * double(p.seg_len - 1);
-                                        const double thc = reduce_2pi(fma(dl, c, th0));
-                                        T sn, cs;
-                                        sincos_t(T(thc), &sn, &cs);
-                                        const cx<T> e = {amp * cs, amp * sn};
-                                        a[u][0].re += e.re;        a[u][0].im += e.im;
-                                        a[u][1].re -= d1 * e.im;   a[u][1].im += d1 * e.re;     // (j dl) e
-                                        a[u][2].re += d2 * e.re;   a[u][2].im += d2 * e.im;     // -(dl^2/2) e
-                                        a[u][3].re += d3 * e.im;   a[u][3].im -= d3 * e.re;     // -j(dl^3/6) e
-                                    }
+                                a0.re += __shfl_xor_sync(0xffffffffu, a0.re, o); a0.im += __shfl_xor_sync(0xffffffffu, a0.im, o);
+                                a1.re += __shfl_xor_sync(0xffffffffu, a1.re, o); a1.im += __shfl_xor_sync(0xffffffffu, a1.im, o);
+                                a2.re += __shfl_xor_sync(0xffffffffu, a2.re, o); a2.im += __shfl_xor_sync(0xffffffffu, a2.im, o);
+                                if (p.porder == 3) { a3.re += __shfl_xor_sync(0xffffffffu, a3.re, o); a3.im += __shfl_xor_sync(0xffffffffu, a3.im, o); }
+                            }
+                            if (sg == 0 && !p.gbar_poly) { gs.re += __shfl_xor_sync(0xffffffffu, gs.re, o); gs.im += __shfl_xor_sync(0xffffffffu, gs.im, o); }
+                        }
+                        if (act && sub == 0) {
+                            if (p.poly) {
+                                cx<T> *c4 = coef + ((l * NR + r) * p.nseg + sg) * 4;
+                                c4[0] = a0; c4[1] = a1; c4[2] = a2; c4[3] = a3;
+                            }
+                            if (sg == 0) {
+                                if (p.gbar_poly) {
+                                    const T m1 = T(p.mu[0][l]), m2 = T(p.mu[1][l]), m3 = T(p.mu[2][l]);
+                                    gs.re = a0.re + m1 * a1.re + m2 * a2.re + m3 * a3.re;
+                                    gs.im = a0.im + m1 * a1.im + m2 * a2.im + m3 * a3.im;
+                                }
+                                gbar[(l * NR + r) * NT + t] = gs;
                             }
                         }
-                        if (p.poly) {
-#pragma unroll
-                            for (int u = 0; u < 4; ++u)
-                                if (sg0 + u < p.nseg) {
-#pragma unroll
-                                    for (int o = 0; o < 4; ++o) {
-                                        const T re = warp_sum(a[u][o].re), im = warp_sum(a[u][o].im);
-                                        if (lane == 0) coef[((l * NR + r) * p.nseg + sg0 + u) * 4 + o] = {re, im};
-                                    }
-                                }
-                        }
                     }
-                    const T gre = warp_sum(gsum.re), gim = warp_sum(gsum.im);
-                    if (lane == 0) gbar[(l * NR + r) * NT + t] = {gre, gim};
                 }
                 // ---------------- B: IFFT (result lands in E.body), cyclic prefix, ISI tail
                 fft_stockham<T, true>(in, other, tw, fft, p.lg);
@@ -318,44 +390,95 @@ ofdm_tdl_kernel(const __grid_constant__ OfdmP p, const Modem m, const cx<T> *__r
                 __syncthreads();
 
                 // ---------------- D: time-varying sparse FIR, accumulate into Y[r]
-                if (p.poly) {
-                    const T half_seg = T(0.5) * T(p.seg_len - 1);
-                    for (int jb0 = 0; jb0 * kOT < fft; jb0 += kJBC) {
+                if (p.poly && p.nseg == 1 && (fft & (kOT * kJBC - 1)) == 0) {
+                    // fast path (one segment, fft a multiple of 1024): no per-sample branches
+                    const T tau0 = T(tid) - T(0.5) * T(fft - 1);
+                    const cx<T> *xb = E + mem + cp + tid;
+                    for (int jo0 = 0; jo0 < fft; jo0 += kOT * kJBC) {
                         cx<T> acc[kJBC][NR];
+                        T tau[kJBC];
 #pragma unroll
-                        for (int jb = 0; jb < kJBC; ++jb)
+                        for (int jb = 0; jb < kJBC; ++jb) {
+                            tau[jb] = tau0 + T(jo0 + jb * kOT);
 #pragma unroll
                             for (int r = 0; r < NR; ++r) acc[jb][r] = {T(0), T(0)};
-                        int seg_prev = -1;
-                        cx<T> cf[NR][4];
+                        }
+                        if (p.porder == 3) {
+                            for (int l = 0; l < p.n_taps; ++l) {
+                                const cx<T> *xl = xb + (jo0 - p.delays[l]);
+                                cx<T> cf[NR][4];
+#pragma unroll
+                                for (int r = 0; r < NR; ++r)
+#pragma unroll
+                                    for (int o = 0; o < 4; ++o) cf[r][o] = coef[(l * NR + r) * 4 + o];
+#pragma unroll
+                                for (int jb = 0; jb < kJBC; ++jb) {
+                                    const cx<T> x = xl[jb * kOT];
+#pragma unroll
+                                    for (int r = 0; r < NR; ++r) tap_mac<T, 3>(acc[jb][r], cf[r], tau[jb], x);
+                                }
+                            }
+                        } else {
+                            for (int l = 0; l < p.n_taps; ++l) {
+                                const cx<T> *xl = xb + (jo0 - p.delays[l]);
+                                cx<T> cf[NR][4];
+#pragma unroll
+                                for (int r = 0; r < NR; ++r)
+#pragma unroll
+                                    for (int o = 0; o < 3; ++o) cf[r][o] = coef[(l * NR + r) * 4 + o];
+#pragma unroll
+                                for (int jb = 0; jb < kJBC; ++jb) {
+                                    const cx<T> x = xl[jb * kOT];
+#pragma unroll
+                                    for (int r = 0; r < NR; ++r) tap_mac<T, 2>(acc[jb][r], cf[r], tau[jb], x);
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int jb = 0; jb < kJBC; ++jb) {
+                            const int j = tid + jo0 + jb * kOT;
+#pragma unroll
+                            for (int r = 0; r < NR; ++r) Yp[r][j] = Yp[r][j] + acc[jb][r];
+                        }
+                    }
+                } else if (p.poly) {
+                    const T tau0 = T(tid) - T(0.5) * T(p.seg_len - 1);
+                    const cx<T> *xb = E + mem + cp + tid;
+                    for (int jb0 = 0; jb0 * kOT < fft; jb0 += kJBC) {
+                        cx<T> acc[kJBC][NR];
+                        T tau[kJBC];
+#pragma unroll
+                        for (int jb = 0; jb < kJBC; ++jb) {
+                            const int j = tid + (jb0 + jb) * kOT;
+                            tau[jb] = tau0 + T(((jb0 + jb) * kOT) & (p.seg_len - 1));
+                            (void)j;
+#pragma unroll
+                            for (int r = 0; r < NR; ++r) acc[jb][r] = {T(0), T(0)};
+                        }
                         for (int l = 0; l < p.n_taps; ++l) {
-                            const int d = p.delays[l];
-                            seg_prev = -1;
+                            const cx<T> *xl = xb - p.delays[l];
+                            cx<T> cf[NR][4];
+                            int seg_prev = -1;
 #pragma unroll
                             for (int jb = 0; jb < kJBC; ++jb) {
-                                const int j = tid + (jb0 + jb) * kOT;
-                                if (j < fft) {
-                                    const int seg = j >> p.seg_lg;         // CTA-uniform per jb: seg_len % 256 == 0 or nseg == 1
+                                const int jo = (jb0 + jb) * kOT;
+                                if (jo + tid < fft) {
+                                    const int seg = jo >> p.seg_lg;        // CTA-uniform (seg_len % 256 == 0 or nseg == 1)
                                     if (seg != seg_prev) {
+                                        const cx<T> *c4 = coef + ((l * NR) * p.nseg + seg) * 4;
 #pragma unroll
                                         for (int r = 0; r < NR; ++r)
 #pragma unroll
-                                            for (int o = 0; o < 4; ++o)
-                                                cf[r][o] = coef[((l * NR + r) * p.nseg + seg) * 4 + o];
+                                            for (int o = 0; o < 4; ++o) cf[r][o] = c4[r * p.nseg * 4 + o];
                                         seg_prev = seg;
                                     }
-                                    const cx<T> x = E[mem + cp + j - d];
-                                    const T dt = T(j - seg * p.seg_len - d) - half_seg;
+                                    const cx<T> x = xl[jo];
+                                    if (p.porder == 3) {
 #pragma unroll
-                                    for (int r = 0; r < NR; ++r) {
-                                        cx<T> g;
-                                        g.re = fma(cf[r][3].re, dt, cf[r][2].re);
-                                        g.im = fma(cf[r][3].im, dt, cf[r][2].im);
-                                        g.re = fma(g.re, dt, cf[r][1].re);
-                                        g.im = fma(g.im, dt, cf[r][1].im);
-                                        g.re = fma(g.re, dt, cf[r][0].re);
-                                        g.im = fma(g.im, dt, cf[r][0].im);
-                                        cmac(acc[jb][r], g, x);
+                                        for (int r = 0; r < NR; ++r) tap_mac<T, 3>(acc[jb][r], cf[r], tau[jb], x);
+                                    } else {
+#pragma unroll
+                                        for (int r = 0; r < NR; ++r) tap_mac<T, 2>(acc[jb][r], cf[r], tau[jb], x);
                                     }
                                 }
                             }
@@ -421,50 +544,72 @@ ofdm_tdl_kernel(const __grid_constant__ OfdmP p, const Modem m, const cx<T> *__r
                 if (res != Yp[r]) { W = Yp[r]; Yp[r] = res; }
             }
 
-            // ---------------- G: H_k, equalise / detect, demap, count
-            for (int q = tid; q < p.used; q += kOT) {
-                const int k = bin_of(q, fft, p.used, p.half);
-                cx<T> H[NR][NT];
+            // ---------------- G: H_k = sum_l gbar_l W^(k d_l), equalise / detect, demap, count.
+            // One thread owns the 4 bins k0 + u*fft/4: W^((k0+u fft/4) d) = W^(k0 d) * (-j)^(u d),
+            // so the twiddle product is shared and the other three bins cost only sign swaps.
+            constexpr int NU = (NR * NT <= 4) ? 4 : 1;
+            const int kstride = fft / NU;
+            for (int k0 = tid; k0 < kstride; k0 += kOT) {
+                cx<T> H[NU][NR][NT];
 #pragma unroll
-                for (int r = 0; r < NR; ++r)
-#pragma unroll
-                    for (int t = 0; t < NT; ++t) H[r][t] = {T(0), T(0)};
-                for (int l = 0; l < p.n_taps; ++l) {
-                    const cx<T> w = tw[(k * p.delays[l]) & (fft - 1)];
+                for (int u = 0; u < NU; ++u)
 #pragma unroll
                     for (int r = 0; r < NR; ++r)
 #pragma unroll
-                        for (int t = 0; t < NT; ++t) cmac(H[r][t], gbar[(l * NR + r) * NT + t], w);
-                }
-                cx<T> y[NR];
+                        for (int t = 0; t < NT; ++t) H[u][r][t] = {T(0), T(0)};
+                for (int l = 0; l < p.n_taps; ++l) {
+                    const int d = p.delays[l];
+                    const cx<T> w = tw[(k0 * d) & (fft - 1)];
+                    const cx<T> *gl = gbar + l * NR * NT;
+                    if constexpr (NU == 4) {
+                        switch (d & 3) {                         // CTA-uniform
+                            case 0: hk_accum4<T, NR, NT, 0>(H, gl, w); break;
+                            case 1: hk_accum4<T, NR, NT, 1>(H, gl, w); break;
+                            case 2: hk_accum4<T, NR, NT, 2>(H, gl, w); break;
+                            default: hk_accum4<T, NR, NT, 3>(H, gl, w); break;
+                        }
+                    } else {
 #pragma unroll
-                for (int r = 0; r < NR; ++r) y[r] = rx_scale * Yp[r][k];
-                cx<T> z[NT];
-                if constexpr (NR == 1 && NT == 1) {
-                    z[0] = cdiv(y[0], H[0][0]);                 // OfdmOneTapEqualizer (ofdm.py:510-511)
-                } else {
-                    HermSolver<NT> sol;
-                    sol.template factor_from_channel<cx<T>, NR>(H, NR, p.fnv);
-                    cx<double> b[NT];
+                        for (int r = 0; r < NR; ++r)
+#pragma unroll
+                            for (int t = 0; t < NT; ++t) cmac(H[0][r][t], gl[r * NT + t], w);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < NU; ++u) {
+                    const int k = k0 + u * kstride;
+                    const int q = pos_of(k, fft, p.used, p.half);
+                    if (q < 0) continue;
+                    cx<T> y[NR];
+#pragma unroll
+                    for (int r = 0; r < NR; ++r) y[r] = rx_scale * Yp[r][k];
+                    cx<T> z[NT];
+                    if constexpr (NR == 1 && NT == 1) {
+                        z[0] = cdiv(y[0], H[u][0][0]);              // OfdmOneTapEqualizer (ofdm.py:510-511)
+                    } else {
+                        HermSolver<NT> sol;
+                        sol.template factor_from_channel<cx<T>, NR>(H[u], NR, p.fnv);
+                        cx<double> b[NT];
+#pragma unroll
+                        for (int t = 0; t < NT; ++t) {
+                            b[t] = {0.0, 0.0};
+#pragma unroll
+                            for (int r = 0; r < NR; ++r) cmac_conj(b[t], cvt<double>(H[u][r][t]), cvt<double>(y[r]));
+                        }
+                        sol.solve(b);
+#pragma unroll
+                        for (int t = 0; t < NT; ++t) z[t] = {T(b[t].re * p.snt), T(b[t].im * p.snt)};
+                    }
 #pragma unroll
                     for (int t = 0; t < NT; ++t) {
-                        b[t] = {0.0, 0.0};
-#pragma unroll
-                        for (int r = 0; r < NR; ++r) cmac_conj(b[t], cvt<double>(H[r][t]), cvt<double>(y[r]));
+                        const int a = dsym[q * NT + t];
+                        const int e = demap_symbol<T>(m, tab, z[t]);
+                        sym_err += (e != a);
+                        bit_err += __popc(e ^ a);
+                        const size_t o = size_t(frame) * p.n_data + size_t(s * p.used + q) * NT + t;
+                        if (idx_hat) idx_hat[o] = uint8_t(e);
+                        if (eq_out) eq_out[o] = z[t];
                     }
-                    sol.solve(b);
-#pragma unroll
-                    for (int t = 0; t < NT; ++t) z[t] = {T(b[t].re * p.snt), T(b[t].im * p.snt)};
-                }
-#pragma unroll
-                for (int t = 0; t < NT; ++t) {
-                    const int a = dsym[q * NT + t];
-                    const int e = demap_symbol<T>(m, tab, z[t]);
-                    sym_err += (e != a);
-                    bit_err += __popc(e ^ a);
-                    const size_t o = size_t(frame) * p.n_data + size_t(s * p.used + q) * NT + t;
-                    if (idx_hat) idx_hat[o] = uint8_t(e);
-                    if (eq_out) eq_out[o] = z[t];
                 }
             }
             __syncthreads();
