@@ -147,6 +147,17 @@ int b200phy_tdl_apply(int dtype, const void *x, const void *fading, const double
                       const int32_t *delays, int n_taps, int Nr, int Nt, int64_t N, void *y,
                       void *stream);
 
+/* TdlImpulseResponse.get_freq_response (channels/fading.py:513-536): DFT along the delay axis of the
+ * zero-padded taps for every time sample, evaluated directly on the sparse taps:
+ * out[k][a][n] = sum_l taps[l][a][n] exp(-2 pi i k d_l / fft);  taps dev complex[n_taps][A][N],
+ * out dev complex[fft][A][N], delays host int32[n_taps]. */
+int b200phy_tdl_freq_response(int dtype, const void *taps, const int32_t *delays, int n_taps, int64_t A,
+                              int64_t N, int fft, void *out, void *stream);
+
+/* x[row][col] *= scales[row] in place (tap power scaling fading.py:949-953, path loss
+ * singleuser.py:130-151, Blast 1/sqrt(Nt) mimo.py:639-640).  scales host double[rows], rows <= 64. */
+int b200phy_scale_rows(int dtype, void *x, int rows, int64_t cols, const double *scales, void *stream);
+
 /* OfdmOneTapEqualizer.equalize_data (ofdm.py:515-552) restated as FFT(mean taps):
  * y dev complex[Nr][n_sym*used]; fading as in b200phy_tdl_apply with N = n_sym*(fft+cp);
  * out dev complex[Nt*n_sym*used]: 1x1 -> y/H; otherwise per-subcarrier Blast decode

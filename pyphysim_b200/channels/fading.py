@@ -94,3 +94,255 @@ COST259_HTx = TdlChannelProfile(
     np.array([0., 356., 441., 528., 546., 609., 625., 842., 916., 941., 15000.,
               16172., 16492., 16876., 16882., 16978., 17615., 17827., 17849., 18016.]) * 1e-9,
     'COST259_HT')
+
+
+def _scale_rows(t, scales):
+    """t[row, ...] *= scales[row] on the device (b200phy_scale_rows)."""
+    import ctypes as C
+    lib = _lib.load()
+    sc = np.ascontiguousarray(scales, dtype=np.float64)
+    rows = sc.size
+    _lib.check(lib.b200phy_scale_rows(_lib.F64, _lib.ptr(t), rows, t.numel() // rows,
+                                      sc.ctypes.data_as(C.POINTER(C.c_double)), _lib.cur_stream()))
+    return t
+
+
+class TdlImpulseResponse:
+    """Impulse response of a TDL channel over time (reference: fading.py:356-698).  The sparse tap
+    values live on the device; NumPy views are produced on demand."""
+
+    def __init__(self, tap_values, channel_profile):
+        assert isinstance(channel_profile, TdlChannelProfile)
+        if channel_profile.Ts is None:
+            raise RuntimeError('Channel profile must be discretized')
+        self._channel_profile = channel_profile
+        if D.is_torch(tap_values):
+            self._sparse_dev, self._sparse_np = tap_values, None
+        else:
+            self._sparse_np = np.asarray(tap_values, dtype=complex)
+            self._sparse_dev = None
+        self._tap_values_dense = None
+
+    def _dev(self):
+        if self._sparse_dev is None:
+            self._sparse_dev, _ = D.to_device(self._sparse_np, np.complex128)
+        return self._sparse_dev
+
+    @property
+    def tap_values_sparse(self):
+        if self._sparse_np is None:
+            self._sparse_np = self._sparse_dev.cpu().numpy()
+        return self._sparse_np
+
+    @property
+    def tap_indexes_sparse(self):
+        return self._channel_profile.tap_delays
+
+    @property
+    def Ts(self):
+        return self._channel_profile.Ts
+
+    @property
+    def tap_delays_sparse(self):
+        return self.tap_indexes_sparse * self.Ts
+
+    @property
+    def tap_values(self):
+        """Dense taps, zero-filled, read-only (fading.py:482-511)."""
+        if self._tap_values_dense is None:
+            sp = self.tap_values_sparse
+            dense = np.zeros((int(self.tap_indexes_sparse[-1]) + 1,) + sp.shape[1:], dtype=complex)
+            dense[self.tap_indexes_sparse] = sp
+            dense.flags['WRITEABLE'] = False
+            self._tap_values_dense = dense
+        return self._tap_values_dense
+
+    @property
+    def num_samples(self):
+        shape = self._sparse_dev.shape if self._sparse_dev is not None else self._sparse_np.shape
+        return int(shape[-1])
+
+    @property
+    def channel_profile(self):
+        return self._channel_profile
+
+    def get_freq_response(self, fft_size):
+        """fading.py:513-536: FFT over the delay axis for every time sample -> [fft, ..., N]."""
+        import ctypes as C
+        lib = _lib.load()
+        torch = _lib.torch_cuda()
+        taps = self._dev()
+        delays = np.ascontiguousarray(self.tap_indexes_sparse, dtype=np.int32)
+        n_taps, N = taps.shape[0], taps.shape[-1]
+        A = taps.numel() // (n_taps * N)
+        out = torch.empty((fft_size,) + tuple(taps.shape[1:]), dtype=torch.complex128, device='cuda')
+        _lib.check(lib.b200phy_tdl_freq_response(_lib.F64, _lib.ptr(taps),
+                                                 delays.ctypes.data_as(C.POINTER(C.c_int32)), n_taps, A, N,
+                                                 int(fft_size), _lib.ptr(out), _lib.cur_stream()))
+        return out.cpu().numpy()
+
+    def __mul__(self, value):
+        """fading.py:538-559."""
+        t = self._dev().clone()
+        _scale_rows(t, [float(value)])
+        return TdlImpulseResponse(t, self._channel_profile)
+
+    def __rmul__(self, value):
+        return self * value
+
+    @staticmethod
+    def concatenate_samples(impulse_responses):
+        """fading.py:655-698."""
+        num = len(impulse_responses)
+        if num < 2:
+            if num == 1:
+                return impulse_responses[0]
+            raise ValueError("impulse_responses must contain at least two TdlImpulseResponse objects.")
+        if impulse_responses[0].channel_profile is not impulse_responses[1].channel_profile:
+            raise ValueError("TdlImpulseResponse objects must have the same channel profile object")
+        import torch
+        taps = torch.cat([a._dev() for a in impulse_responses], dim=-1)
+        return TdlImpulseResponse(taps, impulse_responses[0].channel_profile)
+
+
+class TdlChannel:
+    """Tapped-delay-line channel (reference: fading.py:701-1287)."""
+
+    def __init__(self, fading_generator, channel_profile=None, tap_powers_dB=None, tap_delays=None,
+                 Ts=None):
+        if isinstance(fading_generator, fg.JakesSampleGenerator):
+            if Ts is None:
+                Ts = fading_generator.Ts
+            elif Ts != fading_generator.Ts:
+                raise RuntimeError("The provided sampling interval Ts is different from "
+                                   "the one in the Jakes sample generator.")
+        if channel_profile is None:
+            channel_profile = TdlChannelProfile(tap_powers_dB, tap_delays)
+        else:
+            assert isinstance(channel_profile, TdlChannelProfile), \
+                'channel_profile must be an obj of the TdlChannelProfile class'
+        if not channel_profile.is_discretized:
+            if isinstance(fading_generator, fg.RayleighSampleGenerator) and Ts is None:
+                Ts = 1.0
+            assert Ts is not None
+            channel_profile = channel_profile.get_discretize_profile(Ts)
+        elif channel_profile.Ts != Ts and Ts is not None:
+            raise RuntimeError("Channel profile is already discretized, but it does not "
+                               "agree with the discretized parameter Ts")
+        self._channel_profile = channel_profile
+        self._fading_generator = fading_generator
+        self._set_fading_generator_shape(fading_generator.shape)
+        self._last_impulse_response = None
+        self._switched_direction = False
+
+    @property
+    def switched_direction(self):
+        return self._switched_direction
+
+    @switched_direction.setter
+    def switched_direction(self, value):
+        if not isinstance(value, bool):
+            raise TypeError("switched_direction must be a boolean value")
+        self._switched_direction = value
+
+    def set_num_antennas(self, num_rx_antennas, num_tx_antennas):
+        self._set_fading_generator_shape((num_rx_antennas, num_tx_antennas))
+
+    def _set_fading_generator_shape(self, new_shape):
+        if new_shape is None:
+            self._fading_generator.shape = (self.num_taps,)
+        else:
+            self._fading_generator.shape = (self.num_taps,) + tuple(new_shape)
+
+    channel_profile = property(lambda self: self._channel_profile)
+    num_taps = property(lambda self: self._channel_profile.num_taps)
+    num_taps_with_padding = property(lambda self: self._channel_profile.num_taps_with_padding)
+
+    @property
+    def num_tx_antennas(self):
+        s = self._fading_generator.shape
+        return -1 if s is None or len(s) == 1 else s[2]
+
+    @property
+    def num_rx_antennas(self):
+        s = self._fading_generator.shape
+        return -1 if s is None or len(s) == 1 else s[1]
+
+    def generate_impulse_response(self, num_samples=1):
+        """fading.py:908-959: fading samples * sqrt(tap power), kept on the device."""
+        self._fading_generator.generate_more_samples(num_samples)
+        samples = self._fading_generator._device_samples().clone()
+        if samples.dim() == len(self._fading_generator.shape):      # num_samples axis missing
+            samples = samples.unsqueeze(-1)
+        _scale_rows(samples, np.sqrt(self._channel_profile.tap_powers_linear))
+        self._last_impulse_response = TdlImpulseResponse(samples, self._channel_profile)
+
+    def get_last_impulse_response(self):
+        if self._last_impulse_response is None:
+            raise RuntimeError("No impulse response was generated yet")
+        return self._last_impulse_response
+
+    def _prepare_transmit_signal_shape(self, signal):
+        """fading.py:1009-1044: 1-D input is accepted for a single transmit antenna."""
+        shape = self._fading_generator.shape
+        if len(shape) == 1:
+            return signal
+        _, num_rx, num_tx = shape
+        single = num_rx if self.switched_direction else num_tx
+        if single == 1 and signal.dim() == 1:
+            signal = signal.reshape(1, -1)
+        return signal
+
+    def corrupt_data(self, signal):
+        """fading.py:1046-1124: time-varying sparse FIR (b200phy_tdl_apply)."""
+        import ctypes as C
+        lib = _lib.load()
+        torch = _lib.torch_cuda()
+        x, was_np = D.to_device(signal, np.complex128)
+        num_symbols = x.shape[-1]
+        x = self._prepare_transmit_signal_shape(x)
+        self.generate_impulse_response(num_symbols)
+        taps = self._last_impulse_response._dev()
+        delays = np.ascontiguousarray(self._channel_profile.tap_delays, dtype=np.int32)
+        ones = np.ones(delays.size)
+        mem = self.num_taps_with_padding - 1
+        shape = self._fading_generator.shape
+        if len(shape) == 1:
+            Nr = Nt = 1
+            out_shape = (num_symbols + mem,)
+        elif len(shape) == 3:
+            _, num_rx, num_tx = shape
+            if self.switched_direction:
+                taps = taps.permute(0, 2, 1, 3).contiguous()    # roles of the antennas swap
+                Nr, Nt = num_tx, num_rx
+            else:
+                Nr, Nt = num_rx, num_tx
+            out_shape = (Nr, num_symbols + mem)
+            if x.dim() != 2 or x.shape[0] != Nt:
+                raise ValueError("signal must have shape (%d, num_samples)" % Nt)
+        else:  # pragma: no cover
+            raise RuntimeError("Shape of the fading generator of the TdlChannel class must "
+                               "have either 1 (SISO) or 3 (MIMO) dimensions")
+        y = torch.empty(out_shape, dtype=torch.complex128, device='cuda')
+        _lib.check(lib.b200phy_tdl_apply(_lib.F64, _lib.ptr(x.contiguous()), _lib.ptr(taps),
+                                         ones.ctypes.data_as(C.POINTER(C.c_double)),
+                                         delays.ctypes.data_as(C.POINTER(C.c_int32)), delays.size, Nr, Nt,
+                                         num_symbols, _lib.ptr(y), _lib.cur_stream()))
+        return D.from_device(y, was_np)
+
+    def corrupt_data_in_freq_domain(self, signal, fft_size, carrier_indexes=None):
+        """Block-static frequency-domain path (fading.py:1126-1287) — SURVEY.md §8f row next-2,
+        not built yet."""
+        raise NotImplementedError("corrupt_data_in_freq_domain is not implemented in pyphysim_b200 yet "
+                                  "(SURVEY.md §8f next-2)")
+
+
+class TdlMimoChannel(TdlChannel):
+    """fading.py:1290-1333."""
+
+    def __init__(self, fading_generator, channel_profile=None, tap_powers_dB=None, tap_delays=None,
+                 Ts=None):
+        if fading_generator.shape is None or len(fading_generator.shape) != 2:
+            raise RuntimeError("The provided fading_generator for the TdlMimoChannel class"
+                               " must have a shape with two values")
+        super().__init__(fading_generator, channel_profile, tap_powers_dB, tap_delays, Ts)

@@ -76,4 +76,31 @@ template <int NT> struct HermSolver {
     }
 };
 
+// 2x2: closed-form inverse of A = [[a, conj(c)], [c, b]] (no square roots)
+template <> struct HermSolver<2> {
+    double a, b, idet;
+    cx<double> c;
+
+    template <typename HT, int NRMAX>
+    __device__ __forceinline__ void factor_from_channel(const HT (&H)[NRMAX][2], int Nr, double s2) {
+        a = s2; b = s2; c = {0.0, 0.0};
+#pragma unroll
+        for (int r = 0; r < NRMAX; ++r)
+            if (r < Nr) {
+                const cx<double> h0 = cvt<double>(H[r][0]), h1 = cvt<double>(H[r][1]);
+                a += norm2(h0);
+                b += norm2(h1);
+                cmac_conj(c, h1, h0);                    // A[1][0] = sum conj(H[r][1]) H[r][0]
+            }
+        idet = 1.0 / (a * b - norm2(c));
+    }
+
+    __device__ __forceinline__ void solve(cx<double> (&v)[2]) const {
+        const cx<double> v0 = v[0], v1 = v[1];
+        // A^-1 = [[b, -conj(c)], [-c, a]] / det
+        v[0] = {idet * (b * v0.re - (c.re * v1.re + c.im * v1.im)), idet * (b * v0.im - (c.re * v1.im - c.im * v1.re))};
+        v[1] = {idet * (a * v1.re - (c.re * v0.re - c.im * v0.im)), idet * (a * v1.im - (c.re * v0.im + c.im * v0.re))};
+    }
+};
+
 }  // namespace b200phy

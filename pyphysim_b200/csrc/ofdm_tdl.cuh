@@ -118,6 +118,14 @@ __device__ __forceinline__ double reduce_2pi(double th) {
     return fma(-6.283185307179586476925, rint(th * 0.15915494309189533577), th);
 }
 
+// cis(th) for a phase formed in double: reduce in turns (exact rint), then sincospi in T precision
+__device__ __forceinline__ void sincospi_t(float x, float *s, float *c) { sincospif(x, s, c); }
+__device__ __forceinline__ void sincospi_t(double x, double *s, double *c) { sincospi(x, s, c); }
+template <typename T> __device__ __forceinline__ void cis_phase(double th, T *s, T *c) {
+    const double t = th * 0.15915494309189533577;
+    sincospi_t(T(2.0 * (t - rint(t))), s, c);
+}
+
 __device__ __forceinline__ void sincos_t(float x, float *s, float *c) { sincosf(x, s, c); }
 __device__ __forceinline__ void sincos_t(double x, double *s, double *c) { sincos(x, s, c); }
 
@@ -172,27 +180,13 @@ __device__ __forceinline__ void tap_mac(cx<T> &acc, const cx<T> (&cf)[4], T tau,
     cmac(acc, g, x);
 }
 
-// acc += (-j)^E * v for a compile-time E
-template <typename T, int E> __device__ __forceinline__ void add_rot(cx<T> &acc, cx<T> v) {
-    if ((E & 3) == 0) { acc.re += v.re; acc.im += v.im; }
-    else if ((E & 3) == 1) { acc.re += v.im; acc.im -= v.re; }
-    else if ((E & 3) == 2) { acc.re -= v.re; acc.im -= v.im; }
-    else { acc.re -= v.im; acc.im += v.re; }
-}
-
-// H[u] += (-j)^(u D) * gbar_l[r][t] * w for the four bins k0 + u fft/4 (D = tap delay mod 4)
-template <typename T, int NR, int NT, int D>
-__device__ __forceinline__ void hk_accum4(cx<T> (&H)[4][NR][NT], const cx<T> *__restrict__ gl, cx<T> w) {
+// S[C] += gbar_l[r][t] * w for the residue class C = d_l mod 4 of a tap
+template <typename T, int NR, int NT, int C>
+__device__ __forceinline__ void hk_class(cx<T> (&S)[4][NR][NT], const cx<T> *__restrict__ gl, cx<T> w) {
 #pragma unroll
     for (int r = 0; r < NR; ++r)
 #pragma unroll
-        for (int t = 0; t < NT; ++t) {
-            const cx<T> pr = gl[r * NT + t] * w;
-            add_rot<T, 0>(H[0][r][t], pr);
-            add_rot<T, D>(H[1][r][t], pr);
-            add_rot<T, 2 * D>(H[2][r][t], pr);
-            add_rot<T, 3 * D>(H[3][r][t], pr);
-        }
+        for (int t = 0; t < NT; ++t) cmac(S[C][r][t], gl[r * NT + t], w);
 }
 
 template <typename T, bool FUSED, int NR, int NT, bool WSG>
@@ -218,6 +212,8 @@ ofdm_tdl_kernel(const __grid_constant__ OfdmP p, const Modem m, const cx<T> *__r
     OscRec<T> *osc = (OscRec<T> *)take(p.poly ? 0 : sizeof(OscRec<T>) * p.n_taps * NR * p.L);
     cx<T> *tab = (cx<T> *)take(sizeof(cx<T>) * m.M);
     uint8_t *dsym = (uint8_t *)take(NT * p.used);
+    T *ph_phi = (T *)take(sizeof(T) * p.P4);                  // Jakes phases of the current frame
+    T *ph_psi = (T *)take(sizeof(T) * p.P4);
     cx<T> *pool;                                              // NR + 1 buffers of fft samples
     if constexpr (WSG) pool = ws_g + (size_t)blockIdx.x * (NR + 1) * fft;
     else pool = (cx<T> *)take(sizeof(cx<T>) * (NR + 1) * fft);
@@ -242,6 +238,23 @@ ofdm_tdl_kernel(const __grid_constant__ OfdmP p, const Modem m, const cx<T> *__r
 #pragma unroll
         for (int r = 0; r < NR; ++r) Yp[r] = pool + r * fft;
         cx<T> *W = pool + NR * fft;
+
+        // ---------------- phases of all rays of this frame -> shared memory (coalesced / one Philox
+        // block per 4 phases); ordered before their first use by the barrier after P0
+        if constexpr (FUSED) {
+            for (int b = tid; b < (p.P4 >> 2); b += kOT) {
+                const uint4 b1 = rng_block(p.seed, STREAM_CHANNEL, unit, uint64_t(b));
+                const uint4 b2 = rng_block(p.seed, STREAM_CHANNEL, unit, uint64_t((p.P4 >> 2) + b));
+#pragma unroll
+                for (int l = 0; l < 4; ++l) {
+                    ph_phi[4 * b + l] = phase_from_word<T>(lane_of(b1, l));
+                    ph_psi[4 * b + l] = phase_from_word<T>(lane_of(b2, l));
+                }
+            }
+        } else {
+            const T *gp = phi_g + size_t(frame) * p.P, *gq = psi_g + size_t(frame) * p.P;
+            for (int i = tid; i < p.P; i += kOT) { ph_phi[i] = __ldg(gp + i); ph_psi[i] = __ldg(gq + i); }
+        }
 
         for (int s = 0; s < p.n_sym; ++s) {
             const int n_s = s * S;
@@ -313,21 +326,13 @@ ofdm_tdl_kernel(const __grid_constant__ OfdmP p, const Modem m, const cx<T> *__r
                         if (act)
                             for (int o = sub; o < p.L; o += G) {
                                 const int i = ((o * p.n_taps + l) * NR + r) * NT + t;
-                                T phi, psi;
-                                if constexpr (FUSED) {
-                                    phi = phase_from_word<T>(lane_of(rng_block(p.seed, STREAM_CHANNEL, unit, uint64_t(i >> 2)), i & 3));
-                                    const int i2 = p.P4 + i;
-                                    psi = phase_from_word<T>(lane_of(rng_block(p.seed, STREAM_CHANNEL, unit, uint64_t(i2 >> 2)), i2 & 3));
-                                } else {
-                                    phi = __ldg(phi_g + size_t(frame) * p.P + i);
-                                    psi = __ldg(psi_g + size_t(frame) * p.P + i);
-                                }
+                                const T phi = ph_phi[i], psi = ph_psi[i];
                                 const double cphi = (sizeof(T) == 4 && p.cos_f32) ? double(cosf(float(phi))) : cos(double(phi));
                                 const double dl = p.w0 * p.Ts1 * cphi;             // phase step per sample
                                 const double th0 = fma(p.w0 * cphi, p.t0, double(psi));
                                 if (p.poly) {
                                     T sn, cs;
-                                    sincos_t(T(reduce_2pi(fma(dl, cseg, th0))), &sn, &cs);
+                                    cis_phase<T>(fma(dl, cseg, th0), &sn, &cs);
                                     const cx<T> e = {amp * cs, amp * sn};
                                     const T d1 = T(dl), d2 = T(-0.5 * dl * dl);
                                     a0.re += e.re;        a0.im += e.im;
@@ -340,9 +345,8 @@ ofdm_tdl_kernel(const __grid_constant__ OfdmP p, const Modem m, const cx<T> *__r
                                 }
                                 if (sg == 0 && !p.gbar_poly) {
                                     // mean tap over the S samples of this symbol (CP included, ofdm.py:541-548)
-                                    const double mid = reduce_2pi(fma(dl, double(n_s) + 0.5 * double(S - 1), th0));
                                     T sn, cs;
-                                    sincos_t(T(mid), &sn, &cs);
+                                    cis_phase<T>(fma(dl, double(n_s) + 0.5 * double(S - 1), th0), &sn, &cs);
                                     const T g = amp * dirichlet<T>(dl, S);
                                     gs.re += g * cs;
                                     gs.im += g * sn;
@@ -419,6 +423,7 @@ ofdm_tdl_kernel(const __grid_constant__ OfdmP p, const Modem m, const cx<T> *__r
                                 }
                             }
                         } else {
+#pragma unroll 3
                             for (int l = 0; l < p.n_taps; ++l) {
                                 const cx<T> *xl = xb + (jo0 - p.delays[l]);
                                 cx<T> cf[NR][4];
@@ -508,7 +513,7 @@ ofdm_tdl_kernel(const __grid_constant__ OfdmP p, const Modem m, const cx<T> *__r
                             for (int o = 0; o < p.L; ++o) {
                                 const OscRec<T> rec = orec[o];
                                 T sn, cs;
-                                sincos_t(T(reduce_2pi(fma(rec.dl, n0, rec.th0))), &sn, &cs);
+                                cis_phase<T>(fma(rec.dl, n0, rec.th0), &sn, &cs);
                                 cx<T> z = {cs, sn};
 #pragma unroll
                                 for (int i = 0; i < kCH; ++i) {
@@ -550,6 +555,8 @@ ofdm_tdl_kernel(const __grid_constant__ OfdmP p, const Modem m, const cx<T> *__r
             constexpr int NU = (NR * NT <= 4) ? 4 : 1;
             const int kstride = fft / NU;
             for (int k0 = tid; k0 < kstride; k0 += kOT) {
+                // W^((k0 + u fft/4) d) = W^(k0 d) (-j)^(u d): accumulate the taps into 4 residue classes
+                // S_c (c = d mod 4), then H[u] = sum_c (-j)^(u c) S_c is a 4-point DFT per matrix entry.
                 cx<T> H[NU][NR][NT];
 #pragma unroll
                 for (int u = 0; u < NU; ++u)
@@ -563,10 +570,10 @@ ofdm_tdl_kernel(const __grid_constant__ OfdmP p, const Modem m, const cx<T> *__r
                     const cx<T> *gl = gbar + l * NR * NT;
                     if constexpr (NU == 4) {
                         switch (d & 3) {                         // CTA-uniform
-                            case 0: hk_accum4<T, NR, NT, 0>(H, gl, w); break;
-                            case 1: hk_accum4<T, NR, NT, 1>(H, gl, w); break;
-                            case 2: hk_accum4<T, NR, NT, 2>(H, gl, w); break;
-                            default: hk_accum4<T, NR, NT, 3>(H, gl, w); break;
+                            case 0: hk_class<T, NR, NT, 0>(H, gl, w); break;
+                            case 1: hk_class<T, NR, NT, 1>(H, gl, w); break;
+                            case 2: hk_class<T, NR, NT, 2>(H, gl, w); break;
+                            default: hk_class<T, NR, NT, 3>(H, gl, w); break;
                         }
                     } else {
 #pragma unroll
@@ -574,6 +581,20 @@ ofdm_tdl_kernel(const __grid_constant__ OfdmP p, const Modem m, const cx<T> *__r
 #pragma unroll
                             for (int t = 0; t < NT; ++t) cmac(H[0][r][t], gl[r * NT + t], w);
                     }
+                }
+                if constexpr (NU == 4) {
+#pragma unroll
+                    for (int r = 0; r < NR; ++r)
+#pragma unroll
+                        for (int t = 0; t < NT; ++t) {
+                            const cx<T> a0 = H[0][r][t] + H[2][r][t], a1 = H[0][r][t] - H[2][r][t];
+                            const cx<T> a2 = H[1][r][t] + H[3][r][t], a3 = H[1][r][t] - H[3][r][t];
+                            const cx<T> rot = {a3.im, -a3.re};           // -j * a3
+                            H[0][r][t] = a0 + a2;
+                            H[1][r][t] = a1 + rot;
+                            H[2][r][t] = a0 - a2;
+                            H[3][r][t] = a1 - rot;
+                        }
                 }
 #pragma unroll
                 for (int u = 0; u < NU; ++u) {
@@ -634,6 +655,7 @@ template <typename T> size_t ofdm_tdl_smem(const OfdmP &p, int M, int NR, int NT
     s += al(p.poly ? 0 : sizeof(OscRec<T>) * p.n_taps * NR * p.L);
     s += al(sizeof(cx<T>) * M);
     s += al(size_t(NT) * p.used);
+    s += 2 * al(sizeof(T) * p.P4);
     if (!wsg) s += al(sizeof(cx<T>) * (NR + 1) * p.fft);
     return s;
 }

@@ -2,6 +2,8 @@
 // TdlChannel.corrupt_data and OfdmOneTapEqualizer.equalize_data / per-subcarrier Blast.decode.
 // These are the API-parity path (arrays in HBM between stages); the throughput path is the fused
 // kernel in ofdm_tdl.cuh.
+#include <vector>
+
 #include "ofdm_tdl.cuh"
 
 namespace b200phy {
@@ -127,6 +129,36 @@ equalize_kernel(const cx<T> *__restrict__ y, const cx<T> *__restrict__ gbar, Tap
     }
 }
 
+// out[k][a][n] = sum_l taps[l][a][n] W^(k d_l)
+template <typename T>
+__global__ void __launch_bounds__(256)
+freq_response_kernel(const cx<T> *__restrict__ taps, TapTable tt, long long AN, int fft, cx<T> *__restrict__ out) {
+    for (long long it = blockIdx.x * (long long)blockDim.x + threadIdx.x; it < AN * fft;
+         it += (long long)gridDim.x * blockDim.x) {
+        const int k = int(it / AN);
+        const long long an = it % AN;
+        cx<T> acc = {T(0), T(0)};
+        for (int l = 0; l < tt.n_taps; ++l) {
+            double s, c;
+            sincospi(-2.0 * double((long long)k * tt.delays[l] % fft) / double(fft), &s, &c);
+            cmac(acc, taps[size_t(l) * AN + an], mk<T>(T(c), T(s)));
+        }
+        out[it] = acc;
+    }
+}
+
+struct RowScales { int rows; double s[64]; };
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+scale_rows_kernel(cx<T> *x, RowScales rs, long long cols) {
+    for (long long it = blockIdx.x * (long long)blockDim.x + threadIdx.x; it < rs.rows * cols;
+         it += (long long)gridDim.x * blockDim.x) {
+        const T a = T(rs.s[it / cols]);
+        x[it] = a * x[it];
+    }
+}
+
 static int fill_taps(const double *tap_powers, const int32_t *delays, int n_taps, TapTable *tt) {
     if (!tap_powers || !delays) { set_error("tap_powers/delays is NULL"); return B200PHY_ERR_INVALID; }
     if (n_taps < 1 || n_taps > B200PHY_MAX_TAPS) { set_error("n_taps=%d must be in [1, %d]", n_taps, B200PHY_MAX_TAPS); return B200PHY_ERR_UNSUPPORTED; }
@@ -199,6 +231,36 @@ int b200phy_tdl_apply(int dtype, const void *x, const void *fading, const double
     else
         tdl_apply_kernel<double><<<grid, 256, 0, st>>>((const cx<double> *)x, (const cx<double> *)fading, tt, Nr, Nt, N, (cx<double> *)y);
     B200_CHECK_LAUNCH("tdl_apply_kernel");
+    return B200PHY_OK;
+}
+
+int b200phy_tdl_freq_response(int dtype, const void *taps, const int32_t *delays, int n_taps, int64_t A,
+                              int64_t N, int fft, void *out, void *stream) {
+    std::vector<double> ones(n_taps > 0 ? n_taps : 1, 1.0);
+    TapTable tt;
+    int e = fill_taps(ones.data(), delays, n_taps, &tt);
+    if (e) return e;
+    if (fft < 1) { set_error("fft_size must be positive"); return B200PHY_ERR_INVALID; }
+    if (A * N <= 0) return B200PHY_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = blocks_for(A * N * fft, 256);
+    if (dtype == B200PHY_F32) freq_response_kernel<float><<<grid, 256, 0, st>>>((const cx<float> *)taps, tt, A * N, fft, (cx<float> *)out);
+    else freq_response_kernel<double><<<grid, 256, 0, st>>>((const cx<double> *)taps, tt, A * N, fft, (cx<double> *)out);
+    B200_CHECK_LAUNCH("freq_response_kernel");
+    return B200PHY_OK;
+}
+
+int b200phy_scale_rows(int dtype, void *x, int rows, int64_t cols, const double *scales, void *stream) {
+    if (rows < 1 || rows > 64 || !scales) { set_error("scale_rows: rows=%d must be in [1, 64]", rows); return B200PHY_ERR_INVALID; }
+    if (cols <= 0) return B200PHY_OK;
+    RowScales rs;
+    rs.rows = rows;
+    for (int i = 0; i < rows; ++i) rs.s[i] = scales[i];
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = blocks_for(rows * cols, 256);
+    if (dtype == B200PHY_F32) scale_rows_kernel<float><<<grid, 256, 0, st>>>((cx<float> *)x, rs, cols);
+    else scale_rows_kernel<double><<<grid, 256, 0, st>>>((cx<double> *)x, rs, cols);
+    B200_CHECK_LAUNCH("scale_rows_kernel");
     return B200PHY_OK;
 }
 
