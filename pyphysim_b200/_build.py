@@ -42,18 +42,20 @@ def _digest():
     return h.hexdigest()
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, extra_flags=(), lib_path=None, obj_dir=None):
     """Compile every .cu under csrc/ for sm_100a and link libb200phy.so.  Returns the path."""
+    LIB = lib_path or globals()['LIB']
+    OBJ = obj_dir or globals()['OBJ']
     os.makedirs(OBJ, exist_ok=True)
     stamp = os.path.join(OBJ, 'digest')
-    dig = _digest()
+    dig = _digest() + ' '.join(extra_flags)
     if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == dig:
         return LIB
     nvcc = _nvcc()
 
     def compile_one(src):
         obj = os.path.join(OBJ, os.path.basename(src)[:-3] + '.o')
-        cmd = [nvcc] + NVCC_FLAGS + ['-c', src, '-o', obj]
+        cmd = [nvcc] + NVCC_FLAGS + list(extra_flags) + ['-c', src, '-o', obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         log = r.stdout + r.stderr
         with open(obj[:-2] + '.log', 'w') as fh:

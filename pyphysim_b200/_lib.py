@@ -10,7 +10,7 @@ import threading
 import numpy as np
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, 'libb200phy.so')
+LIB_PATH = os.environ.get('B200PHY_LIB') or os.path.join(PKG, 'libb200phy.so')   # override: A/B builds
 
 F32, F64 = 0, 1
 MODEM_TABLE, MODEM_QAM, MODEM_BPSK = 0, 1, 2

@@ -22,6 +22,9 @@
 
 namespace b200phy {
 
+#ifndef B200_OFDM_MINB
+#define B200_OFDM_MINB 3
+#endif
 constexpr int kOT = 256;       // threads per CTA
 constexpr int kJBC = 4;        // outputs per thread per register block in the channel apply
 constexpr int kCH = 8;         // recurrence chunk length
@@ -190,7 +193,7 @@ __device__ __forceinline__ void hk_class(cx<T> (&S)[4][NR][NT], const cx<T> *__r
 }
 
 template <typename T, bool FUSED, int NR, int NT, bool WSG>
-__global__ void __launch_bounds__(kOT, (sizeof(T) == 4 && NR * NT <= 4) ? 3 : 1)
+__global__ void __launch_bounds__(kOT, (sizeof(T) == 4 && NR * NT <= 4) ? B200_OFDM_MINB : 1)
 ofdm_tdl_kernel(const __grid_constant__ OfdmP p, const Modem m, const cx<T> *__restrict__ tab_g,
                 uint64_t first_unit, long long n_units, const uint8_t *__restrict__ idx_g,
                 const T *__restrict__ phi_g, const T *__restrict__ psi_g,
