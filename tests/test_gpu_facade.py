@@ -178,7 +178,7 @@ def test_jakes_generator_matches_reference(golden):
     ray.generate_more_samples(1000)
     s = ray.get_samples()
     assert s.shape == (3, 2, 1000) and abs(np.mean(np.abs(s) ** 2) - 1) < 0.1
-    assert RayleighSampleGenerator().get_samples().shape == ()
+    assert isinstance(RayleighSampleGenerator().get_samples(), complex)     # randn_c() scalar
 
 
 def test_tdl_channel_siso_chain_matches_reference(golden):
