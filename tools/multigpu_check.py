@@ -1,0 +1,62 @@
+#!/usr/bin/env python
+"""Run under torchrun on N GPUs: every rank simulates its shard of one SNR point with the fused links,
+the counters are all-reduced over NCCL, and rank 0 checks them against the unsharded run on one GPU
+(must be bit-identical: the Philox stream is keyed by the global realization index).
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+        --master-port 29511 tools/multigpu_check.py
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+from pyphysim_b200 import distributed as D   # noqa: E402
+from pyphysim_b200 import links              # noqa: E402
+from pyphysim_b200.channels.fading import COST259_TUx   # noqa: E402
+from pyphysim_b200.modulators import QAM, QPSK           # noqa: E402
+
+
+def main():
+    world = D.init()
+    rank = D.rank()
+    ok = True
+    # OFDM 2x2 headline shape
+    Ts = 1.0 / (15e3 * 1024)
+    prof = COST259_TUx.get_discretize_profile(Ts)
+    link = links.OfdmTdlLink(QAM(64), 1024, 72, 1024, Nr=2, Nt=2, tap_powers_linear=prof.tap_powers_linear,
+                             tap_delays=prof.tap_delays, Fd=10.0, Ts=Ts, L=20, noise_var=0.003, seed=77)
+    total = 20001
+    first, count = D.shard(total, first_unit=500)
+    c = torch.zeros(4, dtype=torch.int64, device='cuda')
+    link.run(count, first_unit=first, counters=c)
+    D.allreduce_counters(c)
+    c2 = torch.zeros(4, dtype=torch.int64, device='cuda')
+    f2, n2 = D.shard(10 ** 7 + 3)
+    links.link_alamouti(QPSK(), 0.1, n2, first_unit=f2, counters=c2)
+    D.allreduce_counters(c2)
+    c3 = torch.zeros(4, dtype=torch.int64, device='cuda')
+    f3, n3 = D.shard(10 ** 7 + 1)
+    links.link_siso_flat(QAM(64), 0.03, n3, first_unit=f3, counters=c3)
+    D.allreduce_counters(c3)
+    torch.cuda.synchronize()
+    if rank == 0:
+        ref = link.run(total, first_unit=500)
+        ref2 = links.link_alamouti(QPSK(), 0.1, 10 ** 7 + 3)
+        ref3 = links.link_siso_flat(QAM(64), 0.03, 10 ** 7 + 1)
+        for name, a, b in (('ofdm2x2', c, ref), ('alamouti', c2, ref2), ('siso', c3, ref3)):
+            same = np.array_equal(a.cpu().numpy(), b)
+            ok &= same
+            print('%-9s world=%d sharded=%s single=%s %s' % (name, world, a.cpu().numpy().tolist(), list(b),
+                                                            'OK' if same else 'MISMATCH'))
+    if D.is_initialized():
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == '__main__':
+    main()
