@@ -35,8 +35,10 @@ template <typename T> __device__ __forceinline__ void cmac_conj(cx<T> &acc, cx<T
     acc.im = fma(-a.im, b.re, acc.im);
 }
 // a / b (plain formula; operands here are O(1) so no scaling is needed)
+__device__ __forceinline__ float recip(float x) { return __frcp_rn(x); }     // correctly rounded, no div sequence
+__device__ __forceinline__ double recip(double x) { return 1.0 / x; }
 template <typename T> __device__ __forceinline__ cx<T> cdiv(cx<T> a, cx<T> b) {
-    T d = T(1) / (b.re * b.re + b.im * b.im);
+    T d = recip(b.re * b.re + b.im * b.im);
     return {(a.re * b.re + a.im * b.im) * d, (a.im * b.re - a.re * b.im) * d};
 }
 template <typename T, typename S> __device__ __forceinline__ cx<T> cvt(cx<S> a) { return {T(a.re), T(a.im)}; }
@@ -50,6 +52,8 @@ struct Modem {
     int side;     // QAM: L = sqrt(M)
     int hbits;    // QAM: log2(L)
     double scale; // QAM: sqrt(2(M-1)/3) (fundamental.py:712-716)
+    float hscale, hside;   // 0.5*scale and 0.5*L in float, for the slicer
+    unsigned m1, m2, m4;   // masks that keep the Gray -> binary shifts inside each half of the index
 };
 
 __host__ inline int ilog2(int v) { int b = 0; while ((1 << b) < v) ++b; return b; }
@@ -62,6 +66,12 @@ __host__ inline Modem make_modem(int kind, int M) {
         m.hbits = m.bits / 2; m.side = 1 << m.hbits;
         m.scale = sqrt((M - 1) * 2.0 / 3.0);
     }
+    m.hscale = float(0.5 * m.scale); m.hside = float(0.5 * m.side);
+    // bit b of each half may only receive bits b+1.. of the SAME half
+    const unsigned half = (1u << m.hbits) - 1u;
+    m.m1 = ((half >> 1) << m.hbits) | (half >> 1);
+    m.m2 = ((half >> 2) << m.hbits) | (half >> 2);
+    m.m4 = ((half >> 4) << m.hbits) | (half >> 4);
     return m;
 }
 
@@ -81,12 +91,23 @@ __device__ __forceinline__ cx<T> map_symbol(const Modem &m, const cx<T> *__restr
 template <typename T>
 __device__ __forceinline__ int demap_symbol(const Modem &m, const cx<T> *__restrict__ tab, cx<T> r) {
     if (m.kind == B200PHY_MODEM_QAM) {
-        const T sc = T(m.scale), L = T(m.side);
-        int jj = int(floor((r.re * sc + L) * T(0.5)));
-        int ii = int(floor((L - r.im * sc) * T(0.5)));
+        int jj, ii;
+        if constexpr (sizeof(T) == 4) {
+            jj = __float2int_rd(fmaf(r.re, m.hscale, m.hside));
+            ii = __float2int_rd(fmaf(-r.im, m.hscale, m.hside));
+        } else {
+            const T sc = T(m.scale), L = T(m.side);
+            jj = int(floor((r.re * sc + L) * T(0.5)));
+            ii = int(floor((L - r.im * sc) * T(0.5)));
+        }
         jj = min(max(jj, 0), m.side - 1);
         ii = min(max(ii, 0), m.side - 1);
-        return (ungray8(ii) << m.hbits) | ungray8(jj);
+        // Gray -> binary of both halves at once (gray2binary, util/conversion.py:252-279)
+        unsigned g = (unsigned(ii) << m.hbits) | unsigned(jj);
+        g ^= (g >> 4) & m.m4;
+        g ^= (g >> 2) & m.m2;
+        g ^= (g >> 1) & m.m1;
+        return int(g);
     }
     if (m.kind == B200PHY_MODEM_BPSK) {
         // NumPy orders complex numbers lexicographically: (r < 0) == re<0 or (re==0 and im<0)

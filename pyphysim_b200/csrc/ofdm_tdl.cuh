@@ -23,10 +23,13 @@
 namespace b200phy {
 
 #ifndef B200_OFDM_MINB
-#define B200_OFDM_MINB 3
+#define B200_OFDM_MINB 4       /* A/B on B200: 4 CTAs/SM (64 regs) is 2-3 % ahead of 3 CTAs (80 regs) */
 #endif
 constexpr int kOT = 256;       // threads per CTA
-constexpr int kJBC = 4;        // outputs per thread per register block in the channel apply
+#ifndef B200_OFDM_JBC
+#define B200_OFDM_JBC 4
+#endif
+constexpr int kJBC = B200_OFDM_JBC;   // outputs per thread per register block in the channel apply
 constexpr int kCH = 8;         // recurrence chunk length
 
 struct OfdmP {
@@ -183,6 +186,24 @@ __device__ __forceinline__ void tap_mac(cx<T> &acc, const cx<T> (&cf)[4], T tau,
     cmac(acc, g, x);
 }
 
+// ---- packed FP32 pairs (Blackwell FFMA2: fma.rn.f32x2).  One instruction issues two FMAs; a scalar
+// operand written as pk2(s, s) is folded by ptxas into a broadcast operand (no MOVs), so the FIR inner
+// loop halves its issue slots.  Same rounding as two scalar fmaf.
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pk2(float lo, float hi) {
+    u64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk2(u64 v, float &lo, float &hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
+    u64 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+
 // S[C] += gbar_l[r][t] * w for the residue class C = d_l mod 4 of a tap
 template <typename T, int NR, int NT, int C>
 __device__ __forceinline__ void hk_class(cx<T> (&S)[4][NR][NT], const cx<T> *__restrict__ gl, cx<T> w) {
@@ -234,6 +255,11 @@ ofdm_tdl_kernel(const __grid_constant__ OfdmP p, const Modem m, const cx<T> *__r
     const T sigma = T(p.sigma), tx_scale = T(p.tx_scale), rx_scale = T(p.rx_scale);
     const int n_items = p.n_taps * NR;
     const int G = p.cgrp, sub = tid & (G - 1);
+    // FIR variants: fastD = one segment and fft a multiple of 1024 (branch-free); in float the inner
+    // loop is issued as FFMA2 pairs over two rx antennas (kPackR) or over (re, im) (kPackC, Nr = 1)
+    constexpr bool kPackR = (sizeof(T) == 4) && (NR % 2 == 0);
+    constexpr bool kPackC = (sizeof(T) == 4) && (NR == 1);
+    const bool fastD = p.poly && p.nseg == 1 && (fft & (kOT * kJBC - 1)) == 0;
 
     for (long long frame = blockIdx.x; frame < n_units; frame += gridDim.x) {
         const uint64_t unit = first_unit + uint64_t(frame);
@@ -256,7 +282,32 @@ ofdm_tdl_kernel(const __grid_constant__ OfdmP p, const Modem m, const cx<T> *__r
             }
         } else {
             const T *gp = phi_g + size_t(frame) * p.P, *gq = psi_g + size_t(frame) * p.P;
-            for (int i = tid; i < p.P; i += kOT) { ph_phi[i] = __ldg(gp + i); ph_psi[i] = __ldg(gq + i); }
+            for (int i0 = tid; i0 < p.P; i0 += 4 * kOT) {
+                T a[4], b[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (i0 + u * kOT < p.P) { a[u] = __ldg(gp + i0 + u * kOT); b[u] = __ldg(gq + i0 + u * kOT); }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (i0 + u * kOT < p.P) { ph_phi[i0 + u * kOT] = a[u]; ph_psi[i0 + u * kOT] = b[u]; }
+            }
+            // pull the next frame of this CTA towards L2 while this one is being computed
+            const long long nf = frame + gridDim.x;
+            if (nf < n_units) {
+                const char *q0 = reinterpret_cast<const char *>(noise_g + size_t(nf) * NR * size_t(p.N + mem));
+                const size_t nb = sizeof(cx<T>) * NR * size_t(p.N + mem);
+                for (size_t o = size_t(tid) * 128; o < nb; o += size_t(kOT) * 128)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(q0 + o));
+                const char *q1 = reinterpret_cast<const char *>(phi_g + size_t(nf) * p.P);
+                const char *q2 = reinterpret_cast<const char *>(psi_g + size_t(nf) * p.P);
+                for (size_t o = size_t(tid) * 128; o < sizeof(T) * p.P; o += size_t(kOT) * 128) {
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(q1 + o));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(q2 + o));
+                }
+                const char *q3 = reinterpret_cast<const char *>(idx_g + size_t(nf) * p.n_data);
+                for (size_t o = size_t(tid) * 128; o < size_t(p.n_data); o += size_t(kOT) * 128)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(q3 + o));
+            }
         }
 
         for (int s = 0; s < p.n_sym; ++s) {
@@ -300,7 +351,16 @@ ofdm_tdl_kernel(const __grid_constant__ OfdmP p, const Modem m, const cx<T> *__r
 #pragma unroll
                     for (int r = 0; r < NR; ++r) {
                         const cx<T> *src = noise_g + (size_t(frame) * NR + r) * rowlen + m0;
-                        for (int j = tid; j < fft; j += kOT) Yp[r][j] = sigma * load_stream(src + j);
+                        // batches of 4 independent loads per thread so one DRAM latency covers them all
+                        for (int j0 = tid; j0 < fft; j0 += 4 * kOT) {
+                            cx<T> v[4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u)
+                                if (j0 + u * kOT < fft) v[u] = load_stream(src + j0 + u * kOT);
+#pragma unroll
+                            for (int u = 0; u < 4; ++u)
+                                if (j0 + u * kOT < fft) Yp[r][j0 + u * kOT] = sigma * v[u];
+                        }
                     }
                 }
             }
@@ -318,6 +378,56 @@ ofdm_tdl_kernel(const __grid_constant__ OfdmP p, const Modem m, const cx<T> *__r
                 }
                 // ---------------- C: per-ray setup for tx antenna t.  G lanes share one (tap, rx) item,
                 // each summing a subset of the L rays; a G-wide shuffle reduction finishes the item.
+                if (fastD && p.gbar_poly) {
+                    // common case (slow fading, one segment): flag-free loop, strength-reduced indices
+                    const int ostride = p.n_taps * NR * NT;
+                    const double wts = p.w0 * p.Ts1, wt0 = p.w0 * p.t0;
+                    for (int it0 = 0; it0 < n_items; it0 += kOT / G) {
+                        const int it = it0 + tid / G;
+                        const bool act = it < n_items;
+                        const int l = act ? it / NR : 0, r = act ? it - l * NR : 0;
+                        const T amp = T(p.amp[l]);
+                        cx<T> a0 = {T(0), T(0)}, a1 = a0, a2 = a0, a3 = a0;
+                        const double cseg = double(n_s + cp - p.delays[l]) + 0.5 * double(fft - 1);
+                        if (act) {
+                            const T *pphi = ph_phi + ((l * NR + r) * NT + t) + sub * ostride;
+                            const T *ppsi = ph_psi + ((l * NR + r) * NT + t) + sub * ostride;
+                            for (int o = sub; o < p.L; o += G, pphi += G * ostride, ppsi += G * ostride) {
+                                const double cphi = (sizeof(T) == 4 && p.cos_f32) ? double(cosf(float(*pphi)))
+                                                                                  : cos(double(*pphi));
+                                const double dl = wts * cphi;
+                                T sn, cs;
+                                cis_phase<T>(fma(dl, cseg, fma(wt0, cphi, double(*ppsi))), &sn, &cs);
+                                const cx<T> e = {amp * cs, amp * sn};
+                                const T d1 = T(dl), d2 = T(-0.5) * d1 * d1, d3 = T(-1.0 / 3.0) * d1 * d2;
+                                a0.re += e.re;        a0.im += e.im;
+                                a1.re -= d1 * e.im;   a1.im += d1 * e.re;     // (j dl) e
+                                a2.re += d2 * e.re;   a2.im += d2 * e.im;     // -(dl^2/2) e
+                                a3.re += d3 * e.im;   a3.im -= d3 * e.re;     // -j(dl^3/6) e
+                            }
+                        }
+                        for (int o = G >> 1; o > 0; o >>= 1) {
+                            a0.re += __shfl_xor_sync(0xffffffffu, a0.re, o); a0.im += __shfl_xor_sync(0xffffffffu, a0.im, o);
+                            a1.re += __shfl_xor_sync(0xffffffffu, a1.re, o); a1.im += __shfl_xor_sync(0xffffffffu, a1.im, o);
+                            a2.re += __shfl_xor_sync(0xffffffffu, a2.re, o); a2.im += __shfl_xor_sync(0xffffffffu, a2.im, o);
+                            a3.re += __shfl_xor_sync(0xffffffffu, a3.re, o); a3.im += __shfl_xor_sync(0xffffffffu, a3.im, o);
+                        }
+                        if (act && sub == 0) {
+                            if (p.porder != 3) a3 = {T(0), T(0)};
+                            if constexpr (kPackR) {
+                                T *cq = reinterpret_cast<T *>(coef) + ((l * (NR / 2) + (r >> 1)) * 4) * 4 + (r & 1);
+                                cq[0] = a0.re; cq[2] = a0.im; cq[4] = a1.re; cq[6] = a1.im;
+                                cq[8] = a2.re; cq[10] = a2.im; cq[12] = a3.re; cq[14] = a3.im;
+                            } else {
+                                cx<T> *c4 = coef + (l * NR + r) * 4;
+                                c4[0] = a0; c4[1] = a1; c4[2] = a2; c4[3] = a3;
+                            }
+                            const T m1 = T(p.mu[0][l]), m2 = T(p.mu[1][l]), m3 = T(p.mu[2][l]);
+                            gbar[(l * NR + r) * NT + t] = {a0.re + m1 * a1.re + m2 * a2.re + m3 * a3.re,
+                                                           a0.im + m1 * a1.im + m2 * a2.im + m3 * a3.im};
+                        }
+                    }
+                } else
                 for (int sg = 0; sg < (p.poly ? p.nseg : 1); ++sg) {
                     for (int it0 = 0; it0 < n_items; it0 += kOT / G) {
                         const int it = it0 + tid / G;
@@ -375,8 +485,20 @@ ofdm_tdl_kernel(const __grid_constant__ OfdmP p, const Modem m, const cx<T> *__r
                         }
                         if (act && sub == 0) {
                             if (p.poly) {
-                                cx<T> *c4 = coef + ((l * NR + r) * p.nseg + sg) * 4;
-                                c4[0] = a0; c4[1] = a1; c4[2] = a2; c4[3] = a3;
+                                if constexpr (kPackR) {
+                                    if (fastD) {
+                                        // rx-pair layout for the FFMA2 FIR: [(tap, pair)][order][re|im][lane]
+                                        T *cq = reinterpret_cast<T *>(coef) + ((l * (NR / 2) + (r >> 1)) * 4) * 4 + (r & 1);
+                                        cq[0] = a0.re; cq[2] = a0.im; cq[4] = a1.re; cq[6] = a1.im;
+                                        cq[8] = a2.re; cq[10] = a2.im; cq[12] = a3.re; cq[14] = a3.im;
+                                    } else {
+                                        cx<T> *c4 = coef + ((l * NR + r) * p.nseg + sg) * 4;
+                                        c4[0] = a0; c4[1] = a1; c4[2] = a2; c4[3] = a3;
+                                    }
+                                } else {
+                                    cx<T> *c4 = coef + ((l * NR + r) * p.nseg + sg) * 4;
+                                    c4[0] = a0; c4[1] = a1; c4[2] = a2; c4[3] = a3;
+                                }
                             }
                             if (sg == 0) {
                                 if (p.gbar_poly) {
@@ -397,7 +519,109 @@ ofdm_tdl_kernel(const __grid_constant__ OfdmP p, const Modem m, const cx<T> *__r
                 __syncthreads();
 
                 // ---------------- D: time-varying sparse FIR, accumulate into Y[r]
-                if (p.poly && p.nseg == 1 && (fft & (kOT * kJBC - 1)) == 0) {
+                if (fastD && kPackR) {
+                    if constexpr (kPackR) {
+                        // FFMA2 over rx pairs: re/im accumulators hold (rx 2p, rx 2p+1)
+                        constexpr int NP = NR / 2;
+                        const float tau0 = float(tid) - 0.5f * float(fft - 1);
+                        const float2 *xb = reinterpret_cast<const float2 *>(E) + mem + cp + tid;
+                        const u64 *cq0 = reinterpret_cast<const u64 *>(coef);
+                        for (int jo0 = 0; jo0 < fft; jo0 += kOT * kJBC) {
+                            u64 aRe[kJBC][NP], aIm[kJBC][NP], tt[kJBC];
+#pragma unroll
+                            for (int jb = 0; jb < kJBC; ++jb) {
+                                const float tau = tau0 + float(jo0 + jb * kOT);
+                                tt[jb] = pk2(tau, tau);
+#pragma unroll
+                                for (int q = 0; q < NP; ++q) { aRe[jb][q] = 0ull; aIm[jb][q] = 0ull; }
+                            }
+#pragma unroll 3
+                            for (int l = 0; l < p.n_taps; ++l) {
+                                const float2 *xl = xb + (jo0 - p.delays[l]);
+                                u64 cR[NP][4], cI[NP][4];
+#pragma unroll
+                                for (int q = 0; q < NP; ++q)
+#pragma unroll
+                                    for (int o = 0; o < 4; ++o) {
+                                        cR[q][o] = cq0[((l * NP + q) * 4 + o) * 2];
+                                        cI[q][o] = cq0[((l * NP + q) * 4 + o) * 2 + 1];
+                                    }
+#pragma unroll
+                                for (int jb = 0; jb < kJBC; ++jb) {
+                                    const float2 x = xl[jb * kOT];
+                                    const u64 xrr = pk2(x.x, x.x), xii = pk2(x.y, x.y), nxii = pk2(-x.y, -x.y);
+#pragma unroll
+                                    for (int q = 0; q < NP; ++q) {
+                                        u64 gR, gI;
+                                        if (p.porder == 3) {
+                                            gR = fma2(cR[q][3], tt[jb], cR[q][2]); gI = fma2(cI[q][3], tt[jb], cI[q][2]);
+                                            gR = fma2(gR, tt[jb], cR[q][1]);       gI = fma2(gI, tt[jb], cI[q][1]);
+                                        } else {
+                                            gR = fma2(cR[q][2], tt[jb], cR[q][1]); gI = fma2(cI[q][2], tt[jb], cI[q][1]);
+                                        }
+                                        gR = fma2(gR, tt[jb], cR[q][0]);
+                                        gI = fma2(gI, tt[jb], cI[q][0]);
+                                        aRe[jb][q] = fma2(gR, xrr, aRe[jb][q]);
+                                        aRe[jb][q] = fma2(gI, nxii, aRe[jb][q]);
+                                        aIm[jb][q] = fma2(gR, xii, aIm[jb][q]);
+                                        aIm[jb][q] = fma2(gI, xrr, aIm[jb][q]);
+                                    }
+                                }
+                            }
+#pragma unroll
+                            for (int jb = 0; jb < kJBC; ++jb) {
+                                const int j = tid + jo0 + jb * kOT;
+#pragma unroll
+                                for (int q = 0; q < NP; ++q) {
+                                    float r0, r1, i0, i1;
+                                    upk2(aRe[jb][q], r0, r1);
+                                    upk2(aIm[jb][q], i0, i1);
+                                    cx<T> *y0 = Yp[2 * q], *y1 = Yp[2 * q + 1];
+                                    y0[j] = y0[j] + mk<T>(T(r0), T(i0));
+                                    y1[j] = y1[j] + mk<T>(T(r1), T(i1));
+                                }
+                            }
+                        }
+                    }
+                } else if (fastD && kPackC) {
+                    if constexpr (kPackC) {
+                        // Nr = 1: FFMA2 over (re, im); g.re / g.im enter as broadcast scalars
+                        const float tau0 = float(tid) - 0.5f * float(fft - 1);
+                        const float2 *xb = reinterpret_cast<const float2 *>(E) + mem + cp + tid;
+                        const u64 *cq0 = reinterpret_cast<const u64 *>(coef);
+                        for (int jo0 = 0; jo0 < fft; jo0 += kOT * kJBC) {
+                            u64 acc2[kJBC], tt[kJBC];
+#pragma unroll
+                            for (int jb = 0; jb < kJBC; ++jb) {
+                                const float tau = tau0 + float(jo0 + jb * kOT);
+                                tt[jb] = pk2(tau, tau);
+                                acc2[jb] = 0ull;
+                            }
+#pragma unroll 3
+                            for (int l = 0; l < p.n_taps; ++l) {
+                                const float2 *xl = xb + (jo0 - p.delays[l]);
+                                const u64 c0 = cq0[l * 4], c1 = cq0[l * 4 + 1], c2 = cq0[l * 4 + 2], c3 = cq0[l * 4 + 3];
+#pragma unroll
+                                for (int jb = 0; jb < kJBC; ++jb) {
+                                    const float2 x = xl[jb * kOT];
+                                    u64 g = (p.porder == 3) ? fma2(fma2(c3, tt[jb], c2), tt[jb], c1) : fma2(c2, tt[jb], c1);
+                                    g = fma2(g, tt[jb], c0);
+                                    float gre, gim;
+                                    upk2(g, gre, gim);
+                                    acc2[jb] = fma2(pk2(x.x, x.y), pk2(gre, gre), acc2[jb]);
+                                    acc2[jb] = fma2(pk2(-x.y, x.x), pk2(gim, gim), acc2[jb]);
+                                }
+                            }
+#pragma unroll
+                            for (int jb = 0; jb < kJBC; ++jb) {
+                                const int j = tid + jo0 + jb * kOT;
+                                float re, im;
+                                upk2(acc2[jb], re, im);
+                                Yp[0][j] = Yp[0][j] + mk<T>(T(re), T(im));
+                            }
+                        }
+                    }
+                } else if (fastD) {
                     // fast path (one segment, fft a multiple of 1024): no per-sample branches
                     const T tau0 = T(tid) - T(0.5) * T(fft - 1);
                     const cx<T> *xb = E + mem + cp + tid;
