@@ -61,21 +61,41 @@ template <typename T> __device__ __forceinline__ void stage_table(const Modem &m
 }
 
 // ================================================================= SISO flat
-template <typename T, bool FUSED>
-__global__ void __launch_bounds__(kThreads)
-siso_flat_kernel(Modem m, const cx<T> *__restrict__ tab_g, int rayleigh, T sigma, uint64_t seed,
+// One realization: r = h*x + sigma*n; r /= h; demap; count.  (notebook Rayleigh cell 8)
+template <typename T, bool RAYLEIGH, bool DEC>
+__device__ __forceinline__ int siso_one(const Modem &m, const cx<T> *tab, int a, cx<T> hh, cx<T> nn, T sigma,
+                                        unsigned &sym_err, unsigned &bit_err, cx<T> *dec_out, long long i) {
+    const cx<T> x = map_symbol<T>(m, tab, a);
+    cx<T> r;
+    if (RAYLEIGH) {
+        r = hh * x + sigma * nn;      // received_data = h * x + n
+        r = cdiv(r, hh);              // received_data /= h
+    } else {
+        r = x + sigma * nn;
+    }
+    const int d = demap_symbol<T>(m, tab, r);
+    sym_err += (d != a);
+    bit_err += __popc(d ^ a);
+    if (DEC) dec_out[i] = r;
+    return d;
+}
+
+template <typename T, bool FUSED, bool RAYLEIGH, bool QAM, bool DEC>
+__global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 5 : 2)
+siso_flat_kernel(Modem m_in, const cx<T> *__restrict__ tab_g, T sigma, uint64_t seed,
                  uint64_t first_unit, long long n, const uint8_t *__restrict__ idx,
                  const cx<T> *__restrict__ h, const cx<T> *__restrict__ noise,
                  uint8_t *__restrict__ idx_hat, cx<T> *__restrict__ dec_out,
                  unsigned long long *counters) {
     __shared__ cx<T> tab[256];
+    Modem m = m_in;
+    if (QAM) m.kind = B200PHY_MODEM_QAM;      // compile-time kind: the slicer is inlined without branches
     stage_table(m, tab_g, tab);
     unsigned sym_err = 0, bit_err = 0;
-    const long long n4 = (n + 3) / 4;
+    const long long n4 = n / 4;               // full groups of 4: branch-free body
     for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < n4;
          g += (long long)gridDim.x * blockDim.x) {
         const long long i0 = g * 4;
-        const int cnt = int(min(4LL, n - i0));
         int a[4];
         cx<T> hh[4], nn[4];
         if constexpr (FUSED) {
@@ -85,54 +105,43 @@ siso_flat_kernel(Modem m, const cx<T> *__restrict__ tab_g, int rayleigh, T sigma
                 a[v] = int(rng_block(seed, STREAM_DATA, unit, 0).x >> (32 - m.bits));
                 const uint4 bn = rng_block(seed, STREAM_NOISE, unit, 0);
                 nn[v] = cnormal<T>(bn.x, bn.y);
-                if (rayleigh) {
+                if (RAYLEIGH) {
                     const uint4 bh = rng_block(seed, STREAM_CHANNEL, unit, 0);
                     hh[v] = cnormal<T>(bh.x, bh.y);
                 }
             }
         } else {
-            if (cnt == 4) {
-                const uchar4 b = __ldg(reinterpret_cast<const uchar4 *>(idx + i0));
-                a[0] = b.x; a[1] = b.y; a[2] = b.z; a[3] = b.w;
-                load_cx<T, 4>(noise + i0, 4, nn);
-                if (rayleigh) load_cx<T, 4>(h + i0, 4, hh);
-            } else {
-#pragma unroll
-                for (int v = 0; v < 4; ++v)
-                    if (v < cnt) {
-                        a[v] = idx[i0 + v];
-                        nn[v] = load1(noise + i0 + v);
-                        if (rayleigh) hh[v] = load1(h + i0 + v);
-                    }
-            }
+            const uchar4 b = __ldg(reinterpret_cast<const uchar4 *>(idx + i0));
+            a[0] = b.x; a[1] = b.y; a[2] = b.z; a[3] = b.w;
+            load_cx<T, 4>(noise + i0, 4, nn);
+            if (RAYLEIGH) load_cx<T, 4>(h + i0, 4, hh);
         }
         int d[4];
 #pragma unroll
-        for (int v = 0; v < 4; ++v) {
-            d[v] = 0;
-            if (v < cnt) {
-                const cx<T> x = map_symbol<T>(m, tab, a[v]);
-                cx<T> r;
-                if (rayleigh) {
-                    r = hh[v] * x + sigma * nn[v];      // received_data = h * x + n
-                    r = cdiv(r, hh[v]);                 // received_data /= h
-                } else {
-                    r = x + sigma * nn[v];
-                }
-                d[v] = demap_symbol<T>(m, tab, r);
-                sym_err += (d[v] != a[v]);
-                bit_err += __popc(d[v] ^ a[v]);
-                if (dec_out) dec_out[i0 + v] = r;
-            }
+        for (int v = 0; v < 4; ++v)
+            d[v] = siso_one<T, RAYLEIGH, DEC>(m, tab, a[v], hh[v], nn[v], sigma, sym_err, bit_err, dec_out, i0 + v);
+        if (idx_hat)
+            *reinterpret_cast<uchar4 *>(idx_hat + i0) =
+                make_uchar4((unsigned char)d[0], (unsigned char)d[1], (unsigned char)d[2], (unsigned char)d[3]);
+    }
+    // ragged tail (n % 4 realizations): one thread each
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+        const long long i = n4 * 4 + threadIdx.x;
+        int a;
+        cx<T> hh = {T(1), T(0)}, nn;
+        if constexpr (FUSED) {
+            const uint64_t unit = first_unit + uint64_t(i);
+            a = int(rng_block(seed, STREAM_DATA, unit, 0).x >> (32 - m.bits));
+            const uint4 bn = rng_block(seed, STREAM_NOISE, unit, 0);
+            nn = cnormal<T>(bn.x, bn.y);
+            if (RAYLEIGH) { const uint4 bh = rng_block(seed, STREAM_CHANNEL, unit, 0); hh = cnormal<T>(bh.x, bh.y); }
+        } else {
+            a = idx[i];
+            nn = load1(noise + i);
+            if (RAYLEIGH) hh = load1(h + i);
         }
-        if (idx_hat) {
-            if (cnt == 4)
-                *reinterpret_cast<uchar4 *>(idx_hat + i0) =
-                    make_uchar4((unsigned char)d[0], (unsigned char)d[1], (unsigned char)d[2],
-                                (unsigned char)d[3]);
-            else
-                for (int v = 0; v < cnt; ++v) idx_hat[i0 + v] = (uint8_t)d[v];
-        }
+        const int d = siso_one<T, RAYLEIGH, DEC>(m, tab, a, hh, nn, sigma, sym_err, bit_err, dec_out, i);
+        if (idx_hat) idx_hat[i] = (uint8_t)d;
     }
     flush_counters(sym_err, bit_err, counters);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -143,9 +152,9 @@ siso_flat_kernel(Modem m, const cx<T> *__restrict__ tab_g, int rayleigh, T sigma
 
 // ================================================================= Alamouti flat
 // One realization per thread: H[Nr][2], S symbols (S/2 codewords), noise[Nr][S].
-template <typename T, bool FUSED>
-__global__ void __launch_bounds__(kThreads)
-alamouti_kernel(Modem m, const cx<T> *__restrict__ tab_g, int Nr, int S, T sigma, uint64_t seed,
+template <typename T, bool FUSED, int NR, bool DEC>
+__global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 4 : 2)
+alamouti_kernel(Modem m, const cx<T> *__restrict__ tab_g, int S, T sigma, uint64_t seed,
                 uint64_t first_unit, long long n, const uint8_t *__restrict__ idx,
                 const cx<T> *__restrict__ Hg, const cx<T> *__restrict__ noise,
                 uint8_t *__restrict__ idx_hat, cx<T> *__restrict__ dec_out,
@@ -157,22 +166,20 @@ alamouti_kernel(Modem m, const cx<T> *__restrict__ tab_g, int Nr, int S, T sigma
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
          i += (long long)gridDim.x * blockDim.x) {
         const uint64_t unit = first_unit + uint64_t(i);
-        cx<T> H[2 * B200PHY_MAX_ANT];        // H[r][t] at 2r+t
+        cx<T> H[2 * NR];                     // H[r][t] at 2r+t
         if constexpr (FUSED) {
 #pragma unroll
-            for (int r = 0; r < B200PHY_MAX_ANT; ++r)
-                if (r < Nr) {
-                    const uint4 b = rng_block(seed, STREAM_CHANNEL, unit, r);
-                    H[2 * r] = cnormal<T>(b.x, b.y);
-                    H[2 * r + 1] = cnormal<T>(b.z, b.w);
-                }
+            for (int r = 0; r < NR; ++r) {
+                const uint4 b = rng_block(seed, STREAM_CHANNEL, unit, r);
+                H[2 * r] = cnormal<T>(b.x, b.y);
+                H[2 * r + 1] = cnormal<T>(b.z, b.w);
+            }
         } else {
-            load_cx<T, 2 * B200PHY_MAX_ANT>(Hg + i * Nr * 2, Nr * 2, H);
+            load_cx<T, 2 * NR>(Hg + i * NR * 2, NR * 2, H);
         }
         T fro = T(0);
 #pragma unroll
-        for (int r = 0; r < B200PHY_MAX_ANT; ++r)
-            if (r < Nr) fro += norm2(H[2 * r]) + norm2(H[2 * r + 1]);
+        for (int r = 0; r < NR; ++r) fro += norm2(H[2 * r]) + norm2(H[2 * r + 1]);
         const T gain = T(1.41421356237309504880) / fro;    // (1/||H||_F^2) * sqrt(2)
         for (int c = 0; c < S / 2; ++c) {
             int a0, a1;
@@ -190,8 +197,7 @@ alamouti_kernel(Modem m, const cx<T> *__restrict__ tab_g, int Nr, int S, T sigma
             const cx<T> x10 = rs2 * s1, x11 = rs2 * conj(s0);
             cx<T> d0 = {T(0), T(0)}, d1 = {T(0), T(0)};
 #pragma unroll
-            for (int r = 0; r < B200PHY_MAX_ANT; ++r)
-                if (r < Nr) {
+            for (int r = 0; r < NR; ++r) {
                     cx<T> n0, n1;
                     if constexpr (FUSED) {
                         // noise row r holds S normals; every row starts on a fresh slot
@@ -199,7 +205,7 @@ alamouti_kernel(Modem m, const cx<T> *__restrict__ tab_g, int Nr, int S, T sigma
                         n0 = cnormal<T>(b.x, b.y);
                         n1 = cnormal<T>(b.z, b.w);
                     } else {
-                        const cx<T> *p = noise + (i * Nr + r) * S + 2 * c;
+                        const cx<T> *p = noise + (i * NR + r) * S + 2 * c;
                         cx<T> t2[2];
                         load_cx<T, 2>(p, 2, t2);
                         n0 = t2[0]; n1 = t2[1];
@@ -220,7 +226,7 @@ alamouti_kernel(Modem m, const cx<T> *__restrict__ tab_g, int Nr, int S, T sigma
             if (idx_hat)
                 *reinterpret_cast<uchar2 *>(idx_hat + i * S + 2 * c) =
                     make_uchar2((unsigned char)e0, (unsigned char)e1);
-            if (dec_out) { dec_out[i * S + 2 * c] = d0; dec_out[i * S + 2 * c + 1] = d1; }
+            if (DEC) { dec_out[i * S + 2 * c] = d0; dec_out[i * S + 2 * c + 1] = d1; }
         }
     }
     flush_counters(sym_err, bit_err, counters);
@@ -362,13 +368,19 @@ static int launch_siso_flat(const Modem &m, const void *table, int rayleigh, dou
                             const void *h, const void *noise, uint8_t *idx_hat, void *dec,
                             int64_t *counters, cudaStream_t st) {
     const bool fused = !idx;
-    const int grid = grid_for((n + 3) / 4);
+    const int grid = grid_for(n / 4 + 1);
     auto args = [&](auto kern) {
-        kern<<<grid, kThreads, 0, st>>>(m, (const cx<T> *)table, rayleigh, T(sqrt(noise_var)), seed, first,
+        kern<<<grid, kThreads, 0, st>>>(m, (const cx<T> *)table, T(sqrt(noise_var)), seed, first,
                                         (long long)n, idx, (const cx<T> *)h, (const cx<T> *)noise,
                                         idx_hat, (cx<T> *)dec, (unsigned long long *)counters);
     };
-    if (fused) args(siso_flat_kernel<T, true>); else args(siso_flat_kernel<T, false>);
+    const bool qam = m.kind == B200PHY_MODEM_QAM;
+#define B200_SISO3(F, R, Q) do { if (dec) args(siso_flat_kernel<T, F, R, Q, true>); else args(siso_flat_kernel<T, F, R, Q, false>); } while (0)
+#define B200_SISO2(F, R) do { if (qam) B200_SISO3(F, R, true); else B200_SISO3(F, R, false); } while (0)
+    if (fused) { if (rayleigh) B200_SISO2(true, true); else B200_SISO2(true, false); }
+    else { if (rayleigh) B200_SISO2(false, true); else B200_SISO2(false, false); }
+#undef B200_SISO2
+#undef B200_SISO3
     B200_CHECK_LAUNCH("siso_flat_kernel");
     return B200PHY_OK;
 }
@@ -381,11 +393,16 @@ static int launch_alamouti(const Modem &m, const void *table, int Nr, int S, dou
     const bool fused = !idx;
     const int grid = grid_for(n);
     auto args = [&](auto kern) {
-        kern<<<grid, kThreads, 0, st>>>(m, (const cx<T> *)table, Nr, S, T(sqrt(noise_var)), seed, first,
+        kern<<<grid, kThreads, 0, st>>>(m, (const cx<T> *)table, S, T(sqrt(noise_var)), seed, first,
                                         (long long)n, idx, (const cx<T> *)H, (const cx<T> *)noise,
                                         idx_hat, (cx<T> *)dec, (unsigned long long *)counters);
     };
-    if (fused) args(alamouti_kernel<T, true>); else args(alamouti_kernel<T, false>);
+#define B200_ALA2(F, N_) do { if (dec) args(alamouti_kernel<T, F, N_, true>); else args(alamouti_kernel<T, F, N_, false>); } while (0)
+#define B200_ALA(F) do { switch (Nr) { case 1: B200_ALA2(F, 1); break; case 2: B200_ALA2(F, 2); break; \
+                                        case 3: B200_ALA2(F, 3); break; default: B200_ALA2(F, 4); } } while (0)
+    if (fused) B200_ALA(true); else B200_ALA(false);
+#undef B200_ALA
+#undef B200_ALA2
     B200_CHECK_LAUNCH("alamouti_kernel");
     return B200PHY_OK;
 }
