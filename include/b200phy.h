@@ -85,7 +85,7 @@ typedef struct b200phy_ofdm_tdl_params {
     int32_t n_taps;       /* discretised profile (channels/fading.py:272-304) */
     int32_t L;            /* Jakes rays (channels/fading_generators.py:319-351) */
     int32_t jakes_mode;   /* B200PHY_JAKES_* */
-    int32_t reserved;
+    int32_t reserved;     /* flags; bit 0 = do not use the antenna-pair FFMA2 kernel (A/B, tests) */
     int32_t delays[B200PHY_MAX_TAPS];    /* tap delays in samples, increasing */
     double tap_powers[B200PHY_MAX_TAPS]; /* linear tap powers */
     double Fd, Ts, t0;    /* Doppler [Hz], sample time [s], time of the frame's first sample */
@@ -153,6 +153,14 @@ int b200phy_tdl_apply(int dtype, const void *x, const void *fading, const double
  * out dev complex[fft][A][N], delays host int32[n_taps]. */
 int b200phy_tdl_freq_response(int dtype, const void *taps, const int32_t *delays, int n_taps, int64_t A,
                               int64_t N, int fft, void *out, void *stream);
+
+/* Block-static frequency-domain channel, TdlChannel.corrupt_data_in_freq_domain (channels/fading.py:
+ * 1126-1287): block b (bs consecutive symbols) is multiplied by the frequency response of the b-th
+ * impulse response at the used carriers: y[r][b*bs+i] = sum_t H[car[i]][r][t][b] * x[t][b*bs+i].
+ * H dev complex[fft][Nr][Nt][B] (b200phy_tdl_freq_response of the per-block taps), x dev complex[Nt][B*bs],
+ * carriers dev int32[bs] or NULL (= 0..fft-1, bs == fft), y dev complex[Nr][B*bs]. */
+int b200phy_freq_apply(int dtype, const void *H, const void *x, const int32_t *carriers, int fft, int bs,
+                       int Nr, int Nt, int64_t B, void *y, void *stream);
 
 /* x[row][col] *= scales[row] in place (tap power scaling fading.py:949-953, path loss
  * singleuser.py:130-151, Blast 1/sqrt(Nt) mimo.py:639-640).  scales host double[rows], rows <= 64. */

@@ -79,3 +79,42 @@ def tdl_corrupt(signal, taps, delays):
             for t in range(Nt):
                 out[:, d:d + N] += taps[i, :, t, :] * signal[t]
     return out
+
+
+def tdl_corrupt_freq(signal, taps, delays, fft_size, carrier_indexes=None):
+    """TdlChannel.corrupt_data_in_freq_domain (fading.py:1126-1287), forward direction: block b of
+    `block_size` symbols is multiplied by the frequency response of the b-th impulse response
+    (taps[..., b], already scaled by sqrt(P)) at the used carriers.
+    SISO: signal[N], taps[taps, B] -> out[N].  MIMO: signal[Nt, N], taps[taps, Nr, Nt, B] -> out[Nr, N]."""
+    from .ofdm import dense_taps
+    car = np.arange(fft_size) if carrier_indexes is None else np.arange(fft_size)[carrier_indexes]
+    bs = car.size
+    N = signal.shape[-1]
+    if N % bs != 0:
+        raise ValueError("The num of elements in `signal` must be a multiple of number of sent "
+                         "elements per `fft_size`.")
+    B = N // bs
+    H = np.fft.fft(dense_taps(taps, delays), fft_size, axis=0)[car]          # [bs, (Nr, Nt,) B]
+    if taps.ndim == 2:
+        out = np.empty(N, dtype=complex)
+        for b in range(B):
+            out[b * bs:(b + 1) * bs] = H[:, b] * signal[b * bs:(b + 1) * bs]
+        return out
+    Nr, Nt = taps.shape[1], taps.shape[2]
+    out = np.zeros((N, Nr), dtype=complex)
+    for b in range(B):
+        for t in range(Nt):
+            out[b * bs:(b + 1) * bs, :] += H[:, :, t, b] * signal[t, b * bs:(b + 1) * bs, np.newaxis]
+    return out.T
+
+
+def jakes_block_samples(phi, psi, Fd, Ts, t0, num_blocks, fft_size):
+    """Fading samples seen by corrupt_data_in_freq_domain: one sample per block, then
+    skip_samples_for_next_generation(fft_size - 1) (fading.py:1203-1276, fading_generators.py:525-540).
+    Returns (h[*shape, num_blocks], new_t0)."""
+    out = []
+    for _ in range(num_blocks):
+        h, t0 = jakes_samples(phi, psi, Fd, Ts, t0, 1)
+        out.append(h)
+        t0 += (fft_size - 1) * Ts
+    return np.concatenate(out, axis=-1), t0

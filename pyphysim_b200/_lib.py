@@ -61,6 +61,7 @@ SIGNATURES = {
     'b200phy_tdl_apply': (C.c_int, [C.c_int, _vp, _vp, _f64p, _i32p, C.c_int, C.c_int, C.c_int,
                                     C.c_int64, _vp, _vp]),
     'b200phy_tdl_freq_response': (C.c_int, [C.c_int, _vp, _i32p, C.c_int, C.c_int64, C.c_int64, C.c_int, _vp, _vp]),
+    'b200phy_freq_apply': (C.c_int, [C.c_int, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, _vp, _vp]),
     'b200phy_scale_rows': (C.c_int, [C.c_int, _vp, C.c_int, C.c_int64, _f64p, _vp]),
     'b200phy_ofdm_equalize': (C.c_int, [C.c_int, _vp, _vp, _f64p, _i32p, C.c_int, C.c_int, C.c_int,
                                         C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, _vp, _vp]),

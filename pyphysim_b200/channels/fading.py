@@ -330,11 +330,87 @@ class TdlChannel:
                                          num_symbols, _lib.ptr(y), _lib.cur_stream()))
         return D.from_device(y, was_np)
 
+    def _generate_block_impulse_responses(self, num_blocks, fft_size):
+        """One impulse-response sample per block, the generator advancing `fft_size` samples per
+        block (generate 1 + skip fft_size-1, fading.py:1203-1276), in ONE device call."""
+        gen = self._fading_generator
+        if isinstance(gen, fg.JakesSampleGenerator):
+            lib = _lib.load()
+            torch = _lib.torch_cuda()
+            t0 = gen._current_time
+            P = int(np.prod(gen._phi_l.shape[1:]))
+            phi = torch.from_numpy(np.ascontiguousarray(gen._phi_l.reshape(gen.L, P))).cuda()
+            psi = torch.from_numpy(np.ascontiguousarray(gen._psi_l.reshape(gen.L, P))).cuda()
+            h = torch.empty((P, num_blocks), dtype=torch.complex128, device='cuda')
+            # block times t0 + b*fft*Ts: the kernel's grid is t0 + n*Ts_eff*1.0000000001
+            _lib.check(lib.b200phy_jakes(_lib.F64, _lib.ptr(phi), _lib.ptr(psi), gen.L, P, num_blocks,
+                                         float(gen.Fd), float(gen.Ts) * fft_size / 1.0000000001, float(t0),
+                                         _lib.ptr(h), _lib.cur_stream()))
+            for _ in range(num_blocks):                 # replay the reference's clock arithmetic
+                gen._advance_clock(1)
+                gen.skip_samples_for_next_generation(fft_size - 1)
+            samples = h.reshape(tuple(gen.shape) + (num_blocks,))
+            gen._store(samples[..., -1:].clone())
+        else:
+            gen.generate_more_samples(num_blocks)
+            samples = gen._device_samples()
+        samples = samples.clone()
+        _scale_rows(samples, np.sqrt(self._channel_profile.tap_powers_linear))
+        self._last_impulse_response = TdlImpulseResponse(samples, self._channel_profile)
+        return samples
+
     def corrupt_data_in_freq_domain(self, signal, fft_size, carrier_indexes=None):
-        """Block-static frequency-domain path (fading.py:1126-1287) — SURVEY.md §8f row next-2,
-        not built yet."""
-        raise NotImplementedError("corrupt_data_in_freq_domain is not implemented in pyphysim_b200 yet "
-                                  "(SURVEY.md §8f next-2)")
+        """Block-static frequency-domain path (fading.py:1126-1287): every block of `fft_size` (or
+        `len(carrier_indexes)`) symbols is multiplied by the frequency response of one impulse response,
+        and the fading generator advances `fft_size` samples per block."""
+        import ctypes as C
+        lib = _lib.load()
+        torch = _lib.torch_cuda()
+        x, was_np = D.to_device(signal, np.complex128)
+        num_symbols = x.shape[-1]
+        x = self._prepare_transmit_signal_shape(x)
+        if carrier_indexes is None:
+            block_size, car = fft_size, None
+        elif isinstance(carrier_indexes, slice):
+            start, stop, step = carrier_indexes.indices(fft_size)
+            block_size = (stop - start) // step         # same expression as the reference (:1170-1172)
+            car = np.arange(fft_size)[carrier_indexes][:block_size]
+        else:
+            car = np.asarray(carrier_indexes)
+            block_size = len(car)
+        if num_symbols % block_size != 0:
+            raise ValueError("The num of elements in `signal` must be a multiple of number of sent "
+                             "elements per `fft_size`.")
+        num_blocks = num_symbols // block_size
+        shape = self._fading_generator.shape
+        taps = self._generate_block_impulse_responses(num_blocks, fft_size)
+        if len(shape) == 1:
+            Nr = Nt = 1
+        else:
+            _, num_rx, num_tx = shape
+            if self.switched_direction:
+                taps = taps.permute(0, 2, 1, 3).contiguous()
+                Nr, Nt = num_tx, num_rx
+            else:
+                Nr, Nt = num_rx, num_tx
+            if x.dim() != 2 or x.shape[0] != Nt:
+                raise ValueError("signal must have shape (%d, num_samples)" % Nt)
+        delays = np.ascontiguousarray(self._channel_profile.tap_delays, dtype=np.int32)
+        H = torch.empty((fft_size, Nr, Nt, num_blocks), dtype=torch.complex128, device='cuda')
+        _lib.check(lib.b200phy_tdl_freq_response(_lib.F64, _lib.ptr(taps),
+                                                 delays.ctypes.data_as(C.POINTER(C.c_int32)), delays.size,
+                                                 Nr * Nt, num_blocks, int(fft_size), _lib.ptr(H),
+                                                 _lib.cur_stream()))
+        car_dev = None
+        if car is not None:
+            car_dev = torch.from_numpy(np.ascontiguousarray(np.mod(car, fft_size), dtype=np.int32)).cuda()
+        y = torch.empty((Nr, num_symbols), dtype=torch.complex128, device='cuda')
+        _lib.check(lib.b200phy_freq_apply(_lib.F64, _lib.ptr(H), _lib.ptr(x.contiguous()), _lib.ptr(car_dev),
+                                          int(fft_size), int(block_size), Nr, Nt, num_blocks, _lib.ptr(y),
+                                          _lib.cur_stream()))
+        if len(shape) == 1:
+            y = y.reshape(num_symbols)
+        return D.from_device(y, was_np)
 
 
 class TdlMimoChannel(TdlChannel):

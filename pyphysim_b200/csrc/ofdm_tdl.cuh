@@ -39,6 +39,7 @@ struct OfdmP {
     int gbar_poly;  // 1: symbol-mean taps from the polynomial moments mu (nseg == 1 only)
     int cos_f32;    // 1: cos(phi) may be evaluated in float (total phase advance is small)
     int cgrp;       // lanes cooperating on one (tap, rx) item in the oscillator setup (power of 2)
+    int no_pair;    // 1: do not use the antenna-pair FFMA2 kernel (A/B and tests)
     int row;        // noise normals per rx row in the Philox layout: 2*ceil((N+mem)/2)
     int P, P4;      // phases per frame, rounded up to a multiple of 4
     int ifft_in_w;  // 1: scatter into W so that the ping-pong IFFT ends in E.body

@@ -1,6 +1,8 @@
 // ofdm_tdl_inst.cuh — defines launch_ofdm_tdl<B200_NR, B200_NT>; included by one .cu per antenna
 // configuration so the (large) kernel instantiations compile in parallel.
-#include "ofdm_tdl.cuh"
+#include <type_traits>
+
+#include "ofdm_tdl_pair.cuh"
 
 namespace b200phy {
 
@@ -37,6 +39,30 @@ static int launch_one(const OfdmP &p, const Modem &m, const void *table, uint64_
     return e;
 }
 
+template <bool FUSED, int NR, int NT>
+static int launch_pair(const OfdmP &p, const Modem &m, const void *table, uint64_t first_unit, int64_t n_units,
+                       const uint8_t *idx, const void *phi, const void *psi, const void *noise,
+                       uint8_t *idx_hat, void *eq_out, int64_t *counters, size_t smem, cudaStream_t st) {
+    auto kern = ofdm_tdl_pair_kernel<FUSED, NR, NT>;
+    int e = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)),
+                       "cudaFuncSetAttribute(ofdm_tdl_pair_kernel)");
+    if (e) return e;
+    int dev = 0, sms = 148, occ = 1;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    e = check_cuda(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kOT, smem),
+                   "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
+    if (e) return e;
+    if (occ < 1) return -1;                       // does not fit: caller falls back to the generic kernel
+    long long grid = (long long)sms * occ;
+    if (grid > n_units) grid = n_units;
+    kern<<<int(grid), kOT, smem, st>>>(p, m, (const cx<float> *)table, first_unit, (long long)n_units, idx,
+                                       (const float *)phi, (const float *)psi, (const cx<float> *)noise,
+                                       idx_hat, (cx<float> *)eq_out, (unsigned long long *)counters);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "ofdm_tdl_pair_kernel launch");
+}
+
 template <typename T, int NR, int NT>
 static int launch_typed(const OfdmP &p, const Modem &m, const void *table, uint64_t first_unit,
                         int64_t n_units, const uint8_t *idx, const void *phi, const void *psi,
@@ -45,6 +71,16 @@ static int launch_typed(const OfdmP &p, const Modem &m, const void *table, uint6
     int dev = 0, max_smem = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if constexpr (std::is_same<T, float>::value && (NR % 2 == 0) && (NT % 2 == 0)) {
+        if (ofdm_tdl_pair_ok(p, NR, NT)) {
+            const size_t ps = ofdm_tdl_pair_smem(p, m.M, NR, NT);
+            if (ps <= size_t(max_smem)) {
+                const int e = idx ? launch_pair<false, NR, NT>(p, m, table, first_unit, n_units, idx, phi, psi, noise, idx_hat, eq_out, counters, ps, st)
+                                  : launch_pair<true, NR, NT>(p, m, table, first_unit, n_units, idx, phi, psi, noise, idx_hat, eq_out, counters, ps, st);
+                if (e >= 0) return e;
+            }
+        }
+    }
     size_t smem = ofdm_tdl_smem<T>(p, m.M, NR, NT, false);
     const bool wsg = smem > size_t(max_smem);
     if (wsg) {

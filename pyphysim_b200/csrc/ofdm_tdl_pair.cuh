@@ -1,0 +1,476 @@
+// ofdm_tdl_pair.cuh — FFMA2 variant of the fused OFDM/TDL link for float, even Nr and even Nt, in the
+// slow-fading regime (POLY, one segment, fft a multiple of 1024): antennas are processed in PAIRS that
+// occupy the two lanes of Blackwell's packed FP32 instructions (fma/add/mul .f32x2).
+//
+// Layout: a "pair sample" is a float4 (a.re, b.re, a.im, b.im) for antennas (a, b) = (2p, 2p+1).
+//   * the IFFT of both tx antennas of a pair and the FFT of both rx antennas of a pair are ONE Stockham
+//     transform on float4 elements: every butterfly add is an FADD2, every twiddle product two FMUL2 +
+//     two FFMA2 with the (scalar) twiddle as a broadcast operand — half the instructions per antenna;
+//   * the FIR reads one float4 per (tap, output) for both tx antennas and accumulates rx pairs with
+//     FFMA2 (coefficients stored as rx pairs), then adds into the rx pair buffer with two FADD2.
+// Semantics, draws, restatements and error bounds are exactly those of ofdm_tdl.cuh (same OfdmP);
+// tests run both kernels against the oracle and against each other.
+#pragma once
+#include "ofdm_tdl.cuh"
+
+namespace b200phy {
+
+__device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ u64 sub2(u64 a, u64 b) { u64 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+
+// pair sample: re = (a.re, b.re), im = (a.im, b.im)
+struct ps { u64 re, im; };
+__device__ __forceinline__ ps ld_ps(const float4 *p) {
+    const float4 v = *p;
+    return {pk2(v.x, v.y), pk2(v.z, v.w)};
+}
+__device__ __forceinline__ void st_ps(float4 *p, ps v) {
+    float a, b, c, d;
+    upk2(v.re, a, b);
+    upk2(v.im, c, d);
+    *p = make_float4(a, b, c, d);
+}
+__device__ __forceinline__ ps operator+(ps a, ps b) { return {add2(a.re, b.re), add2(a.im, b.im)}; }
+__device__ __forceinline__ ps operator-(ps a, ps b) { return {sub2(a.re, b.re), sub2(a.im, b.im)}; }
+// v * w for a scalar complex w (both lanes)
+__device__ __forceinline__ ps mul_w(ps v, float wre, float wim) {
+    const u64 WR = pk2(wre, wre), WI = pk2(wim, wim), NWI = pk2(-wim, -wim);
+    return {fma2(v.im, NWI, mul2(v.re, WR)), fma2(v.im, WR, mul2(v.re, WI))};
+}
+
+// Stockham radix-4 (+ radix-2) FFT on pair samples; same structure as fft_stockham
+template <bool INV>
+__device__ float4 *fft_stockham_pair(float4 *a, float4 *b, const cx<float> *tw, int N, int lg) {
+    float4 *src = a, *dst = b;
+    int Ns = 1;
+    for (int st = 0; st < (lg >> 1); ++st) {
+        __syncthreads();
+        const int q = N >> 2;
+        for (int j = threadIdx.x; j < q; j += blockDim.x) {
+            const int k = j & (Ns - 1);
+            ps v0 = ld_ps(src + j), v1 = ld_ps(src + j + q), v2 = ld_ps(src + j + 2 * q), v3 = ld_ps(src + j + 3 * q);
+            if (Ns > 1) {
+                const int ts = k << (lg - 2 - 2 * st);
+                const cx<float> w1 = tw[ts], w2 = tw[2 * ts], w3 = tw[3 * ts];
+                v1 = mul_w(v1, w1.re, INV ? -w1.im : w1.im);
+                v2 = mul_w(v2, w2.re, INV ? -w2.im : w2.im);
+                v3 = mul_w(v3, w3.re, INV ? -w3.im : w3.im);
+            }
+            const ps a0 = v0 + v2, a1 = v0 - v2, a2 = v1 + v3, a3 = v1 - v3;
+            // forward: a1 -/+ j*a3 -> (re + a3.im, im - a3.re); inverse: signs swapped
+            ps y1, y3;
+            if (INV) { y1 = {sub2(a1.re, a3.im), add2(a1.im, a3.re)}; y3 = {add2(a1.re, a3.im), sub2(a1.im, a3.re)}; }
+            else     { y1 = {add2(a1.re, a3.im), sub2(a1.im, a3.re)}; y3 = {sub2(a1.re, a3.im), add2(a1.im, a3.re)}; }
+            const int j0 = ((j - k) << 2) + k;
+            st_ps(dst + j0, a0 + a2);
+            st_ps(dst + j0 + Ns, y1);
+            st_ps(dst + j0 + 2 * Ns, a0 - a2);
+            st_ps(dst + j0 + 3 * Ns, y3);
+        }
+        Ns <<= 2;
+        float4 *t = src; src = dst; dst = t;
+    }
+    if (lg & 1) {
+        __syncthreads();
+        const int h = N >> 1;
+        for (int j = threadIdx.x; j < h; j += blockDim.x) {
+            const int k = j & (Ns - 1);
+            const cx<float> w = tw[k];
+            const ps v0 = ld_ps(src + j), v1 = mul_w(ld_ps(src + j + h), w.re, INV ? -w.im : w.im);
+            const int j0 = ((j - k) << 1) + k;
+            st_ps(dst + j0, v0 + v1);
+            st_ps(dst + j0 + Ns, v0 - v1);
+        }
+        float4 *t = src; src = dst; dst = t;
+    }
+    __syncthreads();
+    return src;
+}
+
+template <bool FUSED, int NR, int NT>
+__global__ void __launch_bounds__(kOT, (NR * NT <= 4) ? 3 : 1)
+ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m, const cx<float> *__restrict__ tab_g,
+                     uint64_t first_unit, long long n_units, const uint8_t *__restrict__ idx_g,
+                     const float *__restrict__ phi_g, const float *__restrict__ psi_g,
+                     const cx<float> *__restrict__ noise_g, uint8_t *__restrict__ idx_hat,
+                     cx<float> *__restrict__ eq_out, unsigned long long *counters) {
+    using T = float;
+    constexpr int NP = NR / 2, TP = NT / 2;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x;
+    const int fft = p.fft, S = p.S, mem = p.mem, cp = p.cp;
+
+    unsigned char *sp = smem_raw;
+    auto take = [&](size_t bytes) { unsigned char *r = sp; sp += (bytes + 15) & ~size_t(15); return r; };
+    cx<T> *tw = (cx<T> *)take(sizeof(cx<T>) * fft);
+    float4 *E2 = (float4 *)take(sizeof(float4) * (mem + S));            // one tx pair: [tail | cp | body]
+    float4 *body = E2 + mem + cp;
+    float4 *pool = (float4 *)take(sizeof(float4) * (NP + 1) * fft);     // rx pair buffers + 1 scratch
+    cx<T> *gbar = (cx<T> *)take(sizeof(cx<T>) * p.n_taps * NR * NT);
+    float4 *tails = (float4 *)take(p.n_sym > 1 ? sizeof(float4) * TP * mem : 0);
+    u64 *coef = (u64 *)take(sizeof(u64) * p.n_taps * NP * 2 * 4 * 2);   // [tap][rx pair][t in pair][order][re|im]
+    cx<T> *tab = (cx<T> *)take(sizeof(cx<T>) * m.M);
+    uint8_t *dsym = (uint8_t *)take(NT * p.used);
+    T *ph_phi = (T *)take(sizeof(T) * p.P4);
+    T *ph_psi = (T *)take(sizeof(T) * p.P4);
+
+    for (int i = tid; i < fft; i += kOT) {
+        double s, c;
+        sincospi(-2.0 * double(i) / double(fft), &s, &c);
+        tw[i] = {T(c), T(s)};
+    }
+    if (m.kind != B200PHY_MODEM_BPSK)
+        for (int k = tid; k < m.M; k += kOT) tab[k] = tab_g[k];
+    __syncthreads();
+
+    unsigned sym_err = 0, bit_err = 0;
+    const T sigma = T(p.sigma), tx_scale = T(p.tx_scale), rx_scale = T(p.rx_scale);
+    const int n_items = p.n_taps * NR * 2;           // (tap, rx, t in pair)
+    int G = 1;
+    while (G < 16 && (G * 2) * n_items <= kOT) G *= 2;
+    const int sub = tid & (G - 1);
+    const int ostride = p.n_taps * NR * NT;
+    const double wts = p.w0 * p.Ts1, wt0 = p.w0 * p.t0;
+    const bool in_w = p.ifft_in_w != 0;
+
+    for (long long frame = blockIdx.x; frame < n_units; frame += gridDim.x) {
+        const uint64_t unit = first_unit + uint64_t(frame);
+        float4 *Yp[NP];
+#pragma unroll
+        for (int q = 0; q < NP; ++q) Yp[q] = pool + q * fft;
+        float4 *W = pool + NP * fft;
+
+        // ---- phases of all rays of this frame -> shared memory
+        if constexpr (FUSED) {
+            for (int b = tid; b < (p.P4 >> 2); b += kOT) {
+                const uint4 b1 = rng_block(p.seed, STREAM_CHANNEL, unit, uint64_t(b));
+                const uint4 b2 = rng_block(p.seed, STREAM_CHANNEL, unit, uint64_t((p.P4 >> 2) + b));
+#pragma unroll
+                for (int l = 0; l < 4; ++l) {
+                    ph_phi[4 * b + l] = phase_from_word<T>(lane_of(b1, l));
+                    ph_psi[4 * b + l] = phase_from_word<T>(lane_of(b2, l));
+                }
+            }
+        } else {
+            const T *gp = phi_g + size_t(frame) * p.P, *gq = psi_g + size_t(frame) * p.P;
+            for (int i0 = tid; i0 < p.P; i0 += 4 * kOT) {
+                T a[4], b[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (i0 + u * kOT < p.P) { a[u] = __ldg(gp + i0 + u * kOT); b[u] = __ldg(gq + i0 + u * kOT); }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (i0 + u * kOT < p.P) { ph_phi[i0 + u * kOT] = a[u]; ph_psi[i0 + u * kOT] = b[u]; }
+            }
+        }
+
+        for (int s = 0; s < p.n_sym; ++s) {
+            const int n_s = s * S;
+            // ---------------- P0: data symbols, noise into the rx pair buffers
+            {
+                const int w0 = s * p.used * NT, cnt = p.used * NT;
+                if constexpr (FUSED) {
+                    const int b0 = w0 >> 2, b1 = (w0 + cnt - 1) >> 2;
+                    for (int b = b0 + tid; b <= b1; b += kOT) {
+                        const uint4 blk = rng_block(p.seed, STREAM_DATA, unit, uint64_t(b));
+#pragma unroll
+                        for (int l = 0; l < 4; ++l) {
+                            const int w = 4 * b + l - w0;
+                            if (w >= 0 && w < cnt) dsym[w] = uint8_t(lane_of(blk, l) >> (32 - m.bits));
+                        }
+                    }
+                } else {
+                    const uint8_t *src = idx_g + frame * p.n_data + w0;
+                    if ((cnt & 3) == 0 && ((frame * p.n_data + w0) & 3) == 0) {
+                        const uint32_t *s4 = reinterpret_cast<const uint32_t *>(src);
+                        uint32_t *d4 = reinterpret_cast<uint32_t *>(dsym);
+                        for (int i = tid; i < (cnt >> 2); i += kOT) d4[i] = __ldg(s4 + i);
+                    } else {
+                        for (int i = tid; i < cnt; i += kOT) dsym[i] = src[i];
+                    }
+                }
+                const int m0 = n_s + cp;
+                if constexpr (FUSED) {
+                    const int pr0 = m0 >> 1, npr = ((m0 + fft - 1) >> 1) - pr0 + 1;
+                    for (int it = tid; it < NR * npr; it += kOT) {
+                        const int r = it / npr, pr = pr0 + it % npr;
+                        const uint4 blk = rng_block(p.seed, STREAM_NOISE, unit, uint64_t(r) * (p.row >> 1) + pr);
+                        const int j = 2 * pr - m0;
+                        float *yr = reinterpret_cast<float *>(pick(Yp, r >> 1)) + (r & 1);
+                        if (j >= 0 && j < fft) { const cx<T> c = sigma * cnormal<T>(blk.x, blk.y); yr[4 * j] = c.re; yr[4 * j + 2] = c.im; }
+                        if (j + 1 >= 0 && j + 1 < fft) { const cx<T> c = sigma * cnormal<T>(blk.z, blk.w); yr[4 * j + 4] = c.re; yr[4 * j + 6] = c.im; }
+                    }
+                } else {
+                    const size_t rowlen = size_t(p.N + mem);
+#pragma unroll
+                    for (int q = 0; q < NP; ++q) {
+                        const cx<T> *s0 = noise_g + (size_t(frame) * NR + 2 * q) * rowlen + m0, *s1 = s0 + rowlen;
+                        for (int j0 = tid; j0 < fft; j0 += 4 * kOT) {
+                            cx<T> v0[4], v1[4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u)
+                                if (j0 + u * kOT < fft) { v0[u] = load_stream(s0 + j0 + u * kOT); v1[u] = load_stream(s1 + j0 + u * kOT); }
+#pragma unroll
+                            for (int u = 0; u < 4; ++u)
+                                if (j0 + u * kOT < fft)
+                                    Yp[q][j0 + u * kOT] = make_float4(sigma * v0[u].re, sigma * v1[u].re, sigma * v0[u].im, sigma * v1[u].im);
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+
+            for (int tp = 0; tp < TP; ++tp) {
+                // ---------------- A: map + scatter for both antennas of the tx pair
+                float4 *in = in_w ? W : body;
+                float4 *other = in_w ? body : W;
+                for (int k = tid; k < fft; k += kOT) {
+                    const int q = pos_of(k, fft, p.used, p.half);
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (q >= 0) {
+                        const cx<T> s0 = map_symbol<T>(m, tab, dsym[q * NT + 2 * tp]);
+                        const cx<T> s1 = map_symbol<T>(m, tab, dsym[q * NT + 2 * tp + 1]);
+                        v = make_float4(tx_scale * s0.re, tx_scale * s1.re, tx_scale * s0.im, tx_scale * s1.im);
+                    }
+                    in[k] = v;
+                }
+                // ---------------- C: ray setup, items (tap, rx, t in pair), G lanes per item
+                for (int it0 = 0; it0 < n_items; it0 += kOT / G) {
+                    const int it = it0 + tid / G;
+                    const bool act = it < n_items;
+                    const int l = act ? it / (NR * 2) : 0;
+                    const int rem = act ? it - l * NR * 2 : 0;
+                    const int r = rem >> 1, tt = rem & 1, t = 2 * tp + tt;
+                    const T amp = T(p.amp[l]);
+                    cx<T> a0 = {0.f, 0.f}, a1 = a0, a2 = a0, a3 = a0;
+                    const double cseg = double(n_s + cp - p.delays[l]) + 0.5 * double(fft - 1);
+                    if (act) {
+                        const T *pphi = ph_phi + ((l * NR + r) * NT + t) + sub * ostride;
+                        const T *ppsi = ph_psi + ((l * NR + r) * NT + t) + sub * ostride;
+                        for (int o = sub; o < p.L; o += G, pphi += G * ostride, ppsi += G * ostride) {
+                            const double cphi = p.cos_f32 ? double(cosf(*pphi)) : cos(double(*pphi));
+                            const double dl = wts * cphi;
+                            T sn, cs;
+                            cis_phase<T>(fma(dl, cseg, fma(wt0, cphi, double(*ppsi))), &sn, &cs);
+                            const cx<T> e = {amp * cs, amp * sn};
+                            const T d1 = T(dl), d2 = -0.5f * d1 * d1, d3 = (-1.0f / 3.0f) * d1 * d2;
+                            a0.re += e.re;        a0.im += e.im;
+                            a1.re -= d1 * e.im;   a1.im += d1 * e.re;
+                            a2.re += d2 * e.re;   a2.im += d2 * e.im;
+                            a3.re += d3 * e.im;   a3.im -= d3 * e.re;
+                        }
+                    }
+                    for (int o = G >> 1; o > 0; o >>= 1) {
+                        a0.re += __shfl_xor_sync(0xffffffffu, a0.re, o); a0.im += __shfl_xor_sync(0xffffffffu, a0.im, o);
+                        a1.re += __shfl_xor_sync(0xffffffffu, a1.re, o); a1.im += __shfl_xor_sync(0xffffffffu, a1.im, o);
+                        a2.re += __shfl_xor_sync(0xffffffffu, a2.re, o); a2.im += __shfl_xor_sync(0xffffffffu, a2.im, o);
+                        a3.re += __shfl_xor_sync(0xffffffffu, a3.re, o); a3.im += __shfl_xor_sync(0xffffffffu, a3.im, o);
+                    }
+                    if (act && sub == 0) {
+                        if (p.porder != 3) a3 = {0.f, 0.f};
+                        // [(tap, rx pair, tt)][order][re|im][lane = rx & 1]
+                        T *cq = reinterpret_cast<T *>(coef) + (((l * NP + (r >> 1)) * 2 + tt) * 4) * 4 + (r & 1);
+                        cq[0] = a0.re; cq[2] = a0.im; cq[4] = a1.re; cq[6] = a1.im;
+                        cq[8] = a2.re; cq[10] = a2.im; cq[12] = a3.re; cq[14] = a3.im;
+                        const T m1 = T(p.mu[0][l]), m2 = T(p.mu[1][l]), m3 = T(p.mu[2][l]);
+                        gbar[(l * NR + r) * NT + t] = {a0.re + m1 * a1.re + m2 * a2.re + m3 * a3.re,
+                                                       a0.im + m1 * a1.im + m2 * a2.im + m3 * a3.im};
+                    }
+                }
+                // ---------------- B: paired IFFT (ends in E2.body), cyclic prefix, ISI tail
+                fft_stockham_pair<true>(in, other, tw, fft, p.lg);
+                for (int i = tid; i < cp; i += kOT) E2[mem + i] = body[fft - cp + i];
+                for (int i = tid; i < mem; i += kOT)
+                    E2[i] = (s > 0) ? tails[tp * mem + i] : make_float4(0.f, 0.f, 0.f, 0.f);
+                __syncthreads();
+
+                // ---------------- D: FIR for both tx antennas of the pair into the rx pair buffers
+                {
+                    const float tau0 = float(tid) - 0.5f * float(fft - 1);
+                    const float4 *xb = E2 + mem + cp + tid;
+                    for (int jo0 = 0; jo0 < fft; jo0 += kOT * kJBC) {
+                        u64 aRe[kJBC][NP], aIm[kJBC][NP];
+#pragma unroll
+                        for (int jb = 0; jb < kJBC; ++jb)
+#pragma unroll
+                            for (int q = 0; q < NP; ++q) { aRe[jb][q] = 0ull; aIm[jb][q] = 0ull; }
+                        for (int l = 0; l < p.n_taps; ++l) {
+                            const float4 *xl = xb + (jo0 - p.delays[l]);
+                            float4 x4[kJBC];
+#pragma unroll
+                            for (int jb = 0; jb < kJBC; ++jb) x4[jb] = xl[jb * kOT];
+#pragma unroll
+                            for (int tt = 0; tt < 2; ++tt) {
+                                u64 cR[NP][4], cI[NP][4];
+#pragma unroll
+                                for (int q = 0; q < NP; ++q)
+#pragma unroll
+                                    for (int o = 0; o < 4; ++o) {
+                                        cR[q][o] = coef[(((l * NP + q) * 2 + tt) * 4 + o) * 2];
+                                        cI[q][o] = coef[(((l * NP + q) * 2 + tt) * 4 + o) * 2 + 1];
+                                    }
+#pragma unroll
+                                for (int jb = 0; jb < kJBC; ++jb) {
+                                    const float tau = tau0 + float(jo0 + jb * kOT);
+                                    const u64 tt2 = pk2(tau, tau);
+                                    const float xr = tt ? x4[jb].y : x4[jb].x, xi = tt ? x4[jb].w : x4[jb].z;
+                                    const u64 xrr = pk2(xr, xr), xii = pk2(xi, xi), nxii = pk2(-xi, -xi);
+#pragma unroll
+                                    for (int q = 0; q < NP; ++q) {
+                                        u64 gR, gI;
+                                        if (p.porder == 3) {
+                                            gR = fma2(cR[q][3], tt2, cR[q][2]); gI = fma2(cI[q][3], tt2, cI[q][2]);
+                                            gR = fma2(gR, tt2, cR[q][1]);       gI = fma2(gI, tt2, cI[q][1]);
+                                        } else {
+                                            gR = fma2(cR[q][2], tt2, cR[q][1]); gI = fma2(cI[q][2], tt2, cI[q][1]);
+                                        }
+                                        gR = fma2(gR, tt2, cR[q][0]);
+                                        gI = fma2(gI, tt2, cI[q][0]);
+                                        aRe[jb][q] = fma2(gR, xrr, aRe[jb][q]);
+                                        aRe[jb][q] = fma2(gI, nxii, aRe[jb][q]);
+                                        aIm[jb][q] = fma2(gR, xii, aIm[jb][q]);
+                                        aIm[jb][q] = fma2(gI, xrr, aIm[jb][q]);
+                                    }
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int jb = 0; jb < kJBC; ++jb) {
+                            const int j = tid + jo0 + jb * kOT;
+#pragma unroll
+                            for (int q = 0; q < NP; ++q) {
+                                ps y = ld_ps(Yp[q] + j);
+                                y.re = add2(y.re, aRe[jb][q]);
+                                y.im = add2(y.im, aIm[jb][q]);
+                                st_ps(Yp[q] + j, y);
+                            }
+                        }
+                    }
+                }
+                __syncthreads();
+                if (p.n_sym > 1) {
+                    for (int i = tid; i < mem; i += kOT) tails[tp * mem + i] = E2[S + i];
+                    __syncthreads();
+                }
+            }   // tx pairs
+
+            // ---------------- F: paired FFT of every rx pair (rotating pool)
+#pragma unroll
+            for (int q = 0; q < NP; ++q) {
+                float4 *res = fft_stockham_pair<false>(Yp[q], W, tw, fft, p.lg);
+                if (res != Yp[q]) { W = Yp[q]; Yp[q] = res; }
+            }
+
+            // ---------------- G: H_k, detect, demap, count (as in ofdm_tdl.cuh)
+            constexpr int NU = (NR * NT <= 4) ? 4 : 1;
+            const int kstride = fft / NU;
+            for (int k0 = tid; k0 < kstride; k0 += kOT) {
+                cx<T> H[NU][NR][NT];
+#pragma unroll
+                for (int u = 0; u < NU; ++u)
+#pragma unroll
+                    for (int r = 0; r < NR; ++r)
+#pragma unroll
+                        for (int t = 0; t < NT; ++t) H[u][r][t] = {0.f, 0.f};
+                for (int l = 0; l < p.n_taps; ++l) {
+                    const int d = p.delays[l];
+                    const cx<T> w = tw[(k0 * d) & (fft - 1)];
+                    const cx<T> *gl = gbar + l * NR * NT;
+                    if constexpr (NU == 4) {
+                        switch (d & 3) {
+                            case 0: hk_class<T, NR, NT, 0>(H, gl, w); break;
+                            case 1: hk_class<T, NR, NT, 1>(H, gl, w); break;
+                            case 2: hk_class<T, NR, NT, 2>(H, gl, w); break;
+                            default: hk_class<T, NR, NT, 3>(H, gl, w); break;
+                        }
+                    } else {
+#pragma unroll
+                        for (int r = 0; r < NR; ++r)
+#pragma unroll
+                            for (int t = 0; t < NT; ++t) cmac(H[0][r][t], gl[r * NT + t], w);
+                    }
+                }
+                if constexpr (NU == 4) {
+#pragma unroll
+                    for (int r = 0; r < NR; ++r)
+#pragma unroll
+                        for (int t = 0; t < NT; ++t) {
+                            const cx<T> a0 = H[0][r][t] + H[2][r][t], a1 = H[0][r][t] - H[2][r][t];
+                            const cx<T> a2 = H[1][r][t] + H[3][r][t], a3 = H[1][r][t] - H[3][r][t];
+                            const cx<T> rot = {a3.im, -a3.re};
+                            H[0][r][t] = a0 + a2;
+                            H[1][r][t] = a1 + rot;
+                            H[2][r][t] = a0 - a2;
+                            H[3][r][t] = a1 - rot;
+                        }
+                }
+#pragma unroll
+                for (int u = 0; u < NU; ++u) {
+                    const int k = k0 + u * kstride;
+                    const int q = pos_of(k, fft, p.used, p.half);
+                    if (q < 0) continue;
+                    cx<T> y[NR];
+#pragma unroll
+                    for (int qq = 0; qq < NP; ++qq) {
+                        const float4 v = Yp[qq][k];
+                        y[2 * qq] = {rx_scale * v.x, rx_scale * v.z};
+                        y[2 * qq + 1] = {rx_scale * v.y, rx_scale * v.w};
+                    }
+                    HermSolver<NT> sol;
+                    sol.template factor_from_channel<cx<T>, NR>(H[u], NR, p.fnv);
+                    cx<double> b[NT];
+#pragma unroll
+                    for (int t = 0; t < NT; ++t) {
+                        b[t] = {0.0, 0.0};
+#pragma unroll
+                        for (int r = 0; r < NR; ++r) cmac_conj(b[t], cvt<double>(H[u][r][t]), cvt<double>(y[r]));
+                    }
+                    sol.solve(b);
+#pragma unroll
+                    for (int t = 0; t < NT; ++t) {
+                        const cx<T> z = {T(b[t].re * p.snt), T(b[t].im * p.snt)};
+                        const int a = dsym[q * NT + t];
+                        const int e = demap_symbol<T>(m, tab, z);
+                        sym_err += (e != a);
+                        bit_err += __popc(e ^ a);
+                        const size_t o = size_t(frame) * p.n_data + size_t(s * p.used + q) * NT + t;
+                        if (idx_hat) idx_hat[o] = uint8_t(e);
+                        if (eq_out) eq_out[o] = z;
+                    }
+                }
+            }
+            __syncthreads();
+        }   // OFDM symbols
+    }       // frames
+    flush_counters(sym_err, bit_err, counters);
+    if (blockIdx.x == 0 && tid == 0) {
+        atomicAdd(&counters[2], (unsigned long long)n_units * p.n_data);
+        atomicAdd(&counters[3], (unsigned long long)n_units * p.n_data * m.bits);
+    }
+}
+
+inline size_t ofdm_tdl_pair_smem(const OfdmP &p, int M, int NR, int NT) {
+    auto al = [](size_t b) { return (b + 15) & ~size_t(15); };
+    const int NP = NR / 2, TP = NT / 2;
+    size_t s = 0;
+    s += al(sizeof(cx<float>) * p.fft);
+    s += al(sizeof(float4) * (p.mem + p.S));
+    s += al(sizeof(float4) * (NP + 1) * p.fft);
+    s += al(sizeof(cx<float>) * p.n_taps * NR * NT);
+    s += al(p.n_sym > 1 ? sizeof(float4) * TP * p.mem : 0);
+    s += al(sizeof(u64) * p.n_taps * NP * 2 * 4 * 2);
+    s += al(sizeof(cx<float>) * M);
+    s += al(size_t(NT) * p.used);
+    s += 2 * al(sizeof(float) * p.P4);
+    return s;
+}
+
+// the pair kernel applies when: float, even Nr/Nt, POLY with one segment, fft % 1024 == 0, mean taps
+// from the polynomial, and the caller has not disabled it (b200phy_ofdm_tdl_params.reserved bit 0)
+inline bool ofdm_tdl_pair_ok(const OfdmP &p, int NR, int NT) {
+    return (NR % 2 == 0) && (NT % 2 == 0) && p.poly && p.nseg == 1 && (p.fft & (kOT * kJBC - 1)) == 0 &&
+           p.gbar_poly && !p.no_pair;
+}
+
+}  // namespace b200phy

@@ -147,6 +147,25 @@ freq_response_kernel(const cx<T> *__restrict__ taps, TapTable tt, long long AN, 
     }
 }
 
+// y[r][b*bs+i] = sum_t H[car[i]][r][t][b] * x[t][b*bs+i]   (fading.py:1212-1270)
+template <typename T>
+__global__ void __launch_bounds__(256)
+freq_apply_kernel(const cx<T> *__restrict__ H, const cx<T> *__restrict__ x, const int *__restrict__ car,
+                  int bs, int Nr, int Nt, long long B, cx<T> *__restrict__ y) {
+    const long long N = B * bs;
+    for (long long it = blockIdx.x * (long long)blockDim.x + threadIdx.x; it < Nr * N;
+         it += (long long)gridDim.x * blockDim.x) {
+        const int r = int(it / N);
+        const long long n = it % N, b = n / bs;
+        const int i = int(n % bs);
+        const long long k = car ? car[i] : i;
+        cx<T> acc = {T(0), T(0)};
+        for (int t = 0; t < Nt; ++t)
+            cmac(acc, H[((k * Nr + r) * Nt + t) * B + b], x[size_t(t) * N + n]);
+        y[it] = acc;
+    }
+}
+
 struct RowScales { int rows; double s[64]; };
 
 template <typename T>
@@ -247,6 +266,19 @@ int b200phy_tdl_freq_response(int dtype, const void *taps, const int32_t *delays
     if (dtype == B200PHY_F32) freq_response_kernel<float><<<grid, 256, 0, st>>>((const cx<float> *)taps, tt, A * N, fft, (cx<float> *)out);
     else freq_response_kernel<double><<<grid, 256, 0, st>>>((const cx<double> *)taps, tt, A * N, fft, (cx<double> *)out);
     B200_CHECK_LAUNCH("freq_response_kernel");
+    return B200PHY_OK;
+}
+
+int b200phy_freq_apply(int dtype, const void *H, const void *x, const int32_t *carriers, int fft, int bs,
+                       int Nr, int Nt, int64_t B, void *y, void *stream) {
+    if (Nr < 1 || Nt < 1 || bs < 1 || fft < 1) { set_error("freq_apply: bad dimensions"); return B200PHY_ERR_INVALID; }
+    if (!carriers && bs != fft) { set_error("freq_apply: without carrier indexes the block size must equal fft_size"); return B200PHY_ERR_INVALID; }
+    if (B <= 0) return B200PHY_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int grid = blocks_for((long long)Nr * B * bs, 256);
+    if (dtype == B200PHY_F32) freq_apply_kernel<float><<<grid, 256, 0, st>>>((const cx<float> *)H, (const cx<float> *)x, carriers, bs, Nr, Nt, B, (cx<float> *)y);
+    else freq_apply_kernel<double><<<grid, 256, 0, st>>>((const cx<double> *)H, (const cx<double> *)x, carriers, bs, Nr, Nt, B, (cx<double> *)y);
+    B200_CHECK_LAUNCH("freq_apply_kernel");
     return B200PHY_OK;
 }
 

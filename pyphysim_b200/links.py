@@ -38,7 +38,7 @@ class OfdmTdlLink:
     def __init__(self, modulator, fft_size, cp_size, num_used_subcarriers=None, *, num_ofdm_symbols=1,
                  Nr=1, Nt=1, tap_powers_linear, tap_delays, Fd=10.0, Ts=None, L=20, t0=None,
                  noise_var=0.01, filter_noise_var=None, dtype='f32', jakes_mode='auto',
-                 seed=SEED_DEFAULT):
+                 seed=SEED_DEFAULT, use_pair_kernel=True):
         self.modulator = modulator
         self.dtype = _lib.parse_dtype(dtype)
         used = fft_size if num_used_subcarriers is None else num_used_subcarriers
@@ -62,6 +62,7 @@ class OfdmTdlLink:
         p.noise_var = float(noise_var)
         p.filter_noise_var = float(noise_var if filter_noise_var is None else filter_noise_var)
         p.seed = seed
+        p.reserved = 0 if use_pair_kernel else 1      # bit 0: keep to the generic (non-FFMA2-pair) kernel
         self.params = p
         self.mem = int(tap_delays[-1])
         self.N = num_ofdm_symbols * (fft_size + cp_size)

@@ -162,6 +162,30 @@ def test_fused_equals_stream_on_device_draws(dtype, ant):
     assert np.array_equal(c_h, c_f) and np.array_equal(hat_h.numpy(), _t(hat_f))
 
 
+@pytest.mark.parametrize('ant,fft,cp,nsym', [((2, 2), 1024, 72, 2), ((4, 4), 2048, 144, 1), ((4, 2), 1024, 72, 1)])
+def test_pair_kernel_vs_generic_kernel(ant, fft, cp, nsym):
+    """The antenna-pair FFMA2 kernel against the generic kernel (same draws, float): same decisions
+    up to boundary symbols, samples within 1e-5; and its own fused mode == its stream mode."""
+    import torch
+    from pyphysim_b200 import links
+    M = 64 if ant == (2, 2) else 16
+    cfg, pair = make_pair('qam', M, fft, cp, fft, n_sym=nsym, Nr=ant[0], Nt=ant[1], dtype='f32', snr_dB=22.0)
+    gen = links.OfdmTdlLink(pair.modulator, fft, cp, fft, num_ofdm_symbols=nsym, Nr=ant[0], Nt=ant[1],
+                            tap_powers_linear=cfg.tap_powers, tap_delays=cfg.delays, Fd=10.0, Ts=cfg.Ts, L=20,
+                            t0=cfg.t0, noise_var=cfg.noise_var, dtype='f32', seed=SEED, use_pair_kernel=False)
+    n = 12
+    draws = pair.draw(300, n)
+    c_p, hat_p, eq_p = pair.run(n, first_unit=300, draws=draws, want_idx=True, want_eq=True)
+    c_g, hat_g, eq_g = gen.run(n, first_unit=300, draws=draws, want_idx=True, want_eq=True)
+    assert_samples_close(_t(eq_p), _t(eq_g), 2e-5, 'pair vs generic')
+    nbad = assert_decisions(_t(hat_p), _t(hat_g), cfg.modem, _t(eq_g).astype(complex), exact=False, eps=2e-3)
+    assert abs(int(c_p[0]) - int(c_g[0])) <= nbad and c_p[2] == c_g[2]
+    c_f, hat_f = pair.run(n, first_unit=300, want_idx=True)
+    assert np.array_equal(c_f, c_p) and torch.equal(hat_f, hat_p)            # fused == stream, pair kernel
+    # oracle, one frame (full-size frames are slow in NumPy)
+    run_stream_vs_oracle(cfg, pair, np.arange(300, 301), exact=False, rel=1e-4, eps=2e-3)
+
+
 def test_full_size_properties():
     """At BASELINE sizes: noiseless frames decode without error; error rate grows with noise;
     repeatable; totals exact."""
