@@ -171,7 +171,7 @@ def run_reference(args, wname, w):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    per_core = max(1, cpu_sample_size(w) // 4)
+    per_core = max(1, cpu_sample_size(w) // 2)
     vals = []
     for i in range(args.warmup + args.steps):
         v, dt = time_cpu(wname, cores, per_core)
@@ -344,11 +344,21 @@ def main():
                      "frac": achieved / peak_gbs, "traffic": None,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s",
                      "bytes_per_unit": bytes_per_unit, "kernel_ms": ms_kernel,
-                     "note": "OFDM/TDL frames are FP32-issue bound, not HBM bound: see DESIGN.md and profiles/"},
+                     "note": ("OFDM/TDL frames are instruction-issue bound, not HBM bound (see `issue`, DESIGN.md, "
+                              "profiles/)") if w['kind'] == 'ofdm' else "HBM-bound elementwise link"},
         "fused_rng": {"value": world * R / (ms_fused * 1e-3), "unit": "realizations/s", "ms_per_step": ms_fused,
                       "bound": "fp32 issue / SFU (no HBM traffic beyond 32 B of counters)"},
         "e2e": e2e, "gpu_launches": launches, "clocks": sampler.summary(), "counters": final,
     }
+    if wname == DEFAULT:
+        # the real bound of this kernel is instruction issue: instructions per frame come from the
+        # committed ncu capture (profiles/ofdm_tdl_pair_2x2_r01_ncu_metrics.csv), the rate is live
+        wi = 277186414 / 5920.0
+        sm_mhz = line["clocks"].get("sm_mhz") or 1965.0
+        peak_wi = 148 * 4 * sm_mhz * 1e6
+        line["issue"] = {"warp_inst_per_unit": wi, "achieved_warp_inst_per_s": value / world * wi,
+                         "peak_warp_inst_per_s": peak_wi, "frac": value / world * wi / peak_wi,
+                         "source": "ncu smsp__inst_executed.sum, profiles/ofdm_tdl_pair_2x2_r01_ncu_metrics.csv"}
     if not args.no_cpu:
         n1 = cpu_sample_size(w)
         v1, dt1 = time_cpu(wname, 1, n1)

@@ -291,10 +291,13 @@ ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m, const cx<fl
                     const float4 *xb = E2 + mem + cp + tid;
                     for (int jo0 = 0; jo0 < fft; jo0 += kOT * kJBC) {
                         u64 aRe[kJBC][NP], aIm[kJBC][NP];
+                        float tauv[kJBC];
 #pragma unroll
-                        for (int jb = 0; jb < kJBC; ++jb)
+                        for (int jb = 0; jb < kJBC; ++jb) {
+                            tauv[jb] = tau0 + float(jo0 + jb * kOT);
 #pragma unroll
                             for (int q = 0; q < NP; ++q) { aRe[jb][q] = 0ull; aIm[jb][q] = 0ull; }
+                        }
                         for (int l = 0; l < p.n_taps; ++l) {
                             const float4 *xl = xb + (jo0 - p.delays[l]);
                             float4 x4[kJBC];
@@ -312,8 +315,7 @@ ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m, const cx<fl
                                     }
 #pragma unroll
                                 for (int jb = 0; jb < kJBC; ++jb) {
-                                    const float tau = tau0 + float(jo0 + jb * kOT);
-                                    const u64 tt2 = pk2(tau, tau);
+                                    const u64 tt2 = pk2(tauv[jb], tauv[jb]);
                                     const float xr = tt ? x4[jb].y : x4[jb].x, xi = tt ? x4[jb].w : x4[jb].z;
                                     const u64 xrr = pk2(xr, xr), xii = pk2(xi, xi), nxii = pk2(-xi, -xi);
 #pragma unroll
