@@ -144,17 +144,26 @@ def _cpu_worker(args):
 
 
 def cpu_sample_size(w):
-    return {'ofdm': 24 if w.get('Nr', 1) * w.get('Nt', 1) <= 4 else 8, 'siso_flat': 400000,
-            'alamouti': 40000}[w['kind']]
+    """Units for the single-core cpu_baseline leg: about 10-20 s of NumPy work."""
+    return {'ofdm': 256 if w.get('Nr', 1) * w.get('Nt', 1) <= 4 else 32, 'siso_flat': 4000000,
+            'alamouti': 300000}[w['kind']]
 
 
 def time_cpu(wname, cores, units_per_core):
     """Run the oracle port on `cores` processes, disjoint unit slices; returns (units/s, seconds)."""
     import multiprocessing as mp
     jobs = [(wname, i * units_per_core, (i + 1) * units_per_core) for i in range(cores)]
+    # one BLAS/OpenMP thread per process: the workers are the parallelism (set before they start)
+    for var in ('OMP_NUM_THREADS', 'OPENBLAS_NUM_THREADS', 'MKL_NUM_THREADS', 'NUMEXPR_NUM_THREADS'):
+        os.environ[var] = '1'
     t0 = time.perf_counter()
     if cores == 1:
-        res = [_cpu_worker(jobs[0])]
+        try:
+            from threadpoolctl import threadpool_limits
+            with threadpool_limits(limits=1):          # this process's BLAS pool is already up: clamp it
+                res = [_cpu_worker(jobs[0])]
+        except ImportError:
+            res = [_cpu_worker(jobs[0])]
     else:
         with mp.get_context('spawn').Pool(cores) as pool:
             # warm the workers (imports) before timing
@@ -171,7 +180,7 @@ def run_reference(args, wname, w):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    per_core = max(1, cpu_sample_size(w) // 2)
+    per_core = max(1, cpu_sample_size(w) // 16)      # a few seconds per step on every core
     vals = []
     for i in range(args.warmup + args.steps):
         v, dt = time_cpu(wname, cores, per_core)
