@@ -55,19 +55,29 @@ class ClockSampler(threading.Thread):
         self.index, self.rows, self.stop_flag = index, [], False
 
     def run(self):
+        """One persistent `nvidia-smi -lms 50` child: a sample every 50 ms while the timed region runs."""
         q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
              'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
              'clocks_event_reasons.sw_power_cap')
-        while not self.stop_flag:
-            try:
-                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q,
-                                      '--format=csv,noheader,nounits'], capture_output=True, text=True,
-                                     timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(',')])
-            except Exception:
-                pass
-            time.sleep(0.2)
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q,
+                                          '--format=csv,noheader,nounits', '-lms', '50'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            return
+        for line in self.proc.stdout:
+            if self.stop_flag:
+                break
+            parts = [c.strip() for c in line.strip().split(',')]
+            if len(parts) >= 7:
+                self.rows.append(parts)
+
+    def stop(self):
+        self.stop_flag = True
+        proc = getattr(self, 'proc', None)
+        if proc is not None:
+            proc.terminate()
+        self.join(timeout=2)
 
     def summary(self):
         if not self.rows:
@@ -298,6 +308,7 @@ def main():
         full_step()
     sampler = ClockSampler(local)
     sampler.start()
+    time.sleep(0.15)                                   # let the first samples arrive
     l0 = lib.b200phy_launch_count()
     ms_step = timed(full_step, args.steps)
     launches = int(lib.b200phy_launch_count() - l0)
@@ -305,8 +316,7 @@ def main():
     for _ in range(warm):
         fused()
     ms_fused = timed(fused, args.steps)
-    sampler.stop_flag = True
-    sampler.join(timeout=2)
+    sampler.stop()
     final = counters.cpu().numpy().tolist()
 
     # e2e: host buffers -> H2D -> kernel -> D2H through the C entry point (wall clock incl. sync)
