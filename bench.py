@@ -184,12 +184,39 @@ def time_cpu(wname, cores, units_per_core):
     return cores * units_per_core / dt, dt
 
 
+def usable_cores():
+    """Host threads this process may actually run on: affinity mask, capped by the cgroup CPU quota."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    quota = None
+    try:
+        with open('/sys/fs/cgroup/cpu.max') as f:                      # cgroup v2: "<quota|max> <period>"
+            q, per = f.read().split()
+            if q != 'max':
+                quota = float(q) / float(per)
+    except (OSError, ValueError):
+        try:
+            with open('/sys/fs/cgroup/cpu/cpu.cfs_quota_us') as f:     # cgroup v1
+                q = float(f.read())
+            with open('/sys/fs/cgroup/cpu/cpu.cfs_period_us') as f:
+                per = float(f.read())
+            if q > 0:
+                quota = q / per
+        except (OSError, ValueError):
+            pass
+    if quota:
+        n = min(n, max(1, int(quota + 0.5)))
+    return max(1, n)
+
+
 # ------------------------------------------------------------------ reference arm
 def run_reference(args, wname, w):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     per_core = max(1, cpu_sample_size(w) // 16)      # a few seconds per step on every core
     vals = []
     for i in range(args.warmup + args.steps):

@@ -147,6 +147,21 @@ template <typename T> __device__ __forceinline__ cx<T> load_stream(const cx<T> *
     }
 }
 
+// asynchronous global -> shared copies (LDGSTS): the input pipeline of the float pair kernels.  Groups
+// complete in commit order; cp_async_wait<N>() returns when at most N groups are still in flight.
+template <int BYTES> __device__ __forceinline__ void cp_async(void *smem, const void *gmem) {
+    const unsigned s = unsigned(__cvta_generic_to_shared(smem));
+    if constexpr (BYTES == 16)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+    else
+        asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(s), "l"(gmem), "n"(BYTES) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
 template <typename P, int N> __device__ __forceinline__ P pick(P const (&arr)[N], int r) {
     P v = arr[0];
 #pragma unroll

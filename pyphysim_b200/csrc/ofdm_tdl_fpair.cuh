@@ -1,0 +1,401 @@
+// ofdm_tdl_fpair.cuh — FFMA2 variant of the fused OFDM/TDL link for SISO (Nr = Nt = 1), float, in the
+// slow-fading regime: one CTA simulates TWO consecutive frames at once, one per lane of Blackwell's packed
+// FP32 instructions.  A pair sample is a float4 (A.re, B.re, A.im, B.im) for frames (A, B) = (2i, 2i+1):
+// the IFFT / FFT of both frames are one Stockham transform on float4 (ofdm_tdl_pair.cuh), the FIR multiplies
+// lane-wise (coefficient pairs x sample pairs), the one-tap equaliser runs per lane.  Semantics, draws and
+// error bounds are those of ofdm_tdl.cuh; an odd last frame is handled by the generic kernel.
+#pragma once
+#include "ofdm_tdl_pair.cuh"
+
+namespace b200phy {
+
+template <bool FUSED>
+__global__ void __launch_bounds__(kOT, 3)
+ofdm_tdl_fpair_kernel(const __grid_constant__ OfdmP p, const Modem m, const cx<float> *__restrict__ tab_g,
+                      uint64_t first_unit, long long n_pairs, const uint8_t *__restrict__ idx_g,
+                      const float *__restrict__ phi_g, const float *__restrict__ psi_g,
+                      const cx<float> *__restrict__ noise_g, uint8_t *__restrict__ idx_hat,
+                      cx<float> *__restrict__ eq_out, unsigned long long *counters) {
+    using T = float;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x;
+    const int fft = p.fft, S = p.S, mem = p.mem, cp = p.cp;
+
+    unsigned char *sp = smem_raw;
+    auto take = [&](size_t bytes) { unsigned char *r = sp; sp += (bytes + 15) & ~size_t(15); return r; };
+    cx<T> *tw = (cx<T> *)take(sizeof(cx<T>) * fft);
+    float4 *E2 = (float4 *)take(sizeof(float4) * (mem + S));            // [tail | cp | body], lanes = frames
+    float4 *body = E2 + mem + cp;
+    float4 *pool = (float4 *)take(sizeof(float4) * 2 * fft);            // rx buffer + scratch
+    u64 *gbar = (u64 *)take(sizeof(u64) * p.n_taps * 2);                // [tap][re|im], lanes = frames
+    float4 *tails = (float4 *)take(p.n_sym > 1 ? sizeof(float4) * mem : 0);
+    u64 *coef = (u64 *)take(sizeof(u64) * p.n_taps * 4 * 2);            // [tap][order][re|im]
+    cx<T> *tab = (cx<T> *)take(sizeof(cx<T>) * m.M);
+    uint8_t *dsym = (uint8_t *)take(2 * p.used);                        // [frame lane][used]
+    T *ph_phi = (T *)take(sizeof(T) * 2 * p.P4);                        // [frame lane][P4]
+    T *ph_psi = (T *)take(sizeof(T) * 2 * p.P4);
+
+    for (int i = tid; i < fft; i += kOT) {
+        double s, c;
+        sincospi(-2.0 * double(i) / double(fft), &s, &c);
+        tw[i] = {T(c), T(s)};
+    }
+    if (m.kind != B200PHY_MODEM_BPSK)
+        for (int k = tid; k < m.M; k += kOT) tab[k] = tab_g[k];
+    __syncthreads();
+
+    unsigned sym_err = 0, bit_err = 0;
+    const T sigma = T(p.sigma), tx_scale = T(p.tx_scale), rx_scale = T(p.rx_scale);
+    const int n_items = p.n_taps * 2;                // (tap, frame lane)
+    int G = 1;
+    while (G < 16 && (G * 2) * n_items <= kOT) G *= 2;
+    const int sub = tid & (G - 1);
+    const int ostride = p.n_taps;
+    const double wts = p.w0 * p.Ts1, wt0 = p.w0 * p.t0;
+    const bool in_w = p.ifft_in_w != 0;
+    const bool o3 = p.porder == 3;
+
+    // stream-mode input pipeline, as in ofdm_tdl_pair.cuh: next pair's phases by LDGSTS during the FIR, its
+    // data symbols in two registers, raw noise rows into the (unused) rx buffer at frame start
+    const bool pf = !FUSED && p.n_sym == 1 && (p.n_data & 3) == 0 && 2 * p.n_data <= 8 * kOT &&
+                    (reinterpret_cast<uintptr_t>(idx_g) & 7) == 0;
+    const bool pf16 = pf && (p.P & 3) == 0 && aligned16(phi_g) && aligned16(psi_g);
+    const bool apipe = !FUSED && fft == kOT * kJBC;
+    uint2 idx_pre = make_uint2(0u, 0u);
+    auto prefetch = [&](long long f) {               // f = first frame of the pair
+#pragma unroll
+        for (int ln = 0; ln < 2; ++ln) {
+            const T *gp = phi_g + size_t(f + ln) * p.P, *gq = psi_g + size_t(f + ln) * p.P;
+            T *dp = ph_phi + ln * p.P4, *dq = ph_psi + ln * p.P4;
+            if (pf16) {
+                for (int i = tid; i < (p.P >> 2); i += kOT) {
+                    cp_async<16>(dp + 4 * i, gp + 4 * i);
+                    cp_async<16>(dq + 4 * i, gq + 4 * i);
+                }
+            } else {
+                for (int i = tid; i < p.P; i += kOT) {
+                    cp_async<4>(dp + i, gp + i);
+                    cp_async<4>(dq + i, gq + i);
+                }
+            }
+        }
+        if (tid < (p.n_data >> 2)) idx_pre = __ldg(reinterpret_cast<const uint2 *>(idx_g + size_t(f) * p.n_data) + tid);
+    };
+    if constexpr (!FUSED) {
+        if (pf && blockIdx.x < n_pairs) prefetch(2 * (long long)blockIdx.x);
+        cp_async_commit();
+    }
+
+    for (long long pr = blockIdx.x; pr < n_pairs; pr += gridDim.x) {
+        const long long frame = 2 * pr;               // lane 0 = frame, lane 1 = frame + 1
+        float4 *Y = pool, *W = pool + fft;
+
+        // ---- phases of both frames -> shared memory
+        if constexpr (FUSED) {
+            for (int it = tid; it < 2 * (p.P4 >> 2); it += kOT) {
+                const int ln = it / (p.P4 >> 2), b = it - ln * (p.P4 >> 2);
+                const uint64_t unit = first_unit + uint64_t(frame + ln);
+                const uint4 b1 = rng_block(p.seed, STREAM_CHANNEL, unit, uint64_t(b));
+                const uint4 b2 = rng_block(p.seed, STREAM_CHANNEL, unit, uint64_t((p.P4 >> 2) + b));
+#pragma unroll
+                for (int l = 0; l < 4; ++l) {
+                    ph_phi[ln * p.P4 + 4 * b + l] = phase_from_word<T>(lane_of(b1, l));
+                    ph_psi[ln * p.P4 + 4 * b + l] = phase_from_word<T>(lane_of(b2, l));
+                }
+            }
+        } else if (pf) {
+            cp_async_wait<0>();                      // prefetched during the previous pair
+            if (tid < (p.n_data >> 2)) reinterpret_cast<uint2 *>(dsym)[tid] = idx_pre;
+        } else {
+#pragma unroll
+            for (int ln = 0; ln < 2; ++ln)
+                for (int i = tid; i < p.P; i += kOT) {
+                    ph_phi[ln * p.P4 + i] = __ldg(phi_g + size_t(frame + ln) * p.P + i);
+                    ph_psi[ln * p.P4 + i] = __ldg(psi_g + size_t(frame + ln) * p.P + i);
+                }
+        }
+
+        for (int s = 0; s < p.n_sym; ++s) {
+            const int n_s = s * S;
+            // ---------------- P0: data symbols of both frames, noise into Y
+            {
+                const int w0 = s * p.used, cnt = p.used;
+                if constexpr (FUSED) {
+                    const int b0 = w0 >> 2, nb = ((w0 + cnt - 1) >> 2) - b0 + 1;
+                    for (int it = tid; it < 2 * nb; it += kOT) {
+                        const int ln = it / nb, b = b0 + it - ln * nb;
+                        const uint4 blk = rng_block(p.seed, STREAM_DATA, first_unit + uint64_t(frame + ln), uint64_t(b));
+#pragma unroll
+                        for (int l = 0; l < 4; ++l) {
+                            const int w = 4 * b + l - w0;
+                            if (w >= 0 && w < cnt) dsym[ln * p.used + w] = uint8_t(lane_of(blk, l) >> (32 - m.bits));
+                        }
+                    }
+                } else if (!pf) {
+#pragma unroll
+                    for (int ln = 0; ln < 2; ++ln) {
+                        const uint8_t *src = idx_g + size_t(frame + ln) * p.n_data + w0;
+                        for (int i = tid; i < cnt; i += kOT) dsym[ln * p.used + i] = src[i];
+                    }
+                }
+                const int m0 = n_s + cp;
+                if constexpr (FUSED) {
+                    const int pr0 = m0 >> 1, npr = ((m0 + fft - 1) >> 1) - pr0 + 1;
+                    for (int it = tid; it < 2 * npr; it += kOT) {
+                        const int ln = it / npr, q = pr0 + it - ln * npr;
+                        const uint4 blk = rng_block(p.seed, STREAM_NOISE, first_unit + uint64_t(frame + ln), uint64_t(q));
+                        const int j = 2 * q - m0;
+                        float *yr = reinterpret_cast<float *>(Y) + ln;
+                        if (j >= 0 && j < fft) { const cx<T> c = sigma * cnormal<T>(blk.x, blk.y); yr[4 * j] = c.re; yr[4 * j + 2] = c.im; }
+                        if (j + 1 >= 0 && j + 1 < fft) { const cx<T> c = sigma * cnormal<T>(blk.z, blk.w); yr[4 * j + 4] = c.re; yr[4 * j + 6] = c.im; }
+                    }
+                } else if (apipe) {
+                    const size_t rowlen = size_t(p.N + mem);
+                    const cx<T> *s0 = noise_g + size_t(frame) * rowlen + m0, *s1 = s0 + rowlen;
+                    cx<T> *raw = reinterpret_cast<cx<T> *>(Y);
+#pragma unroll
+                    for (int jb = 0; jb < kJBC; ++jb) {
+                        cp_async<8>(raw + tid + jb * kOT, s0 + tid + jb * kOT);
+                        cp_async<8>(raw + fft + tid + jb * kOT, s1 + tid + jb * kOT);
+                    }
+                    cp_async_commit();
+                } else {
+                    const size_t rowlen = size_t(p.N + mem);
+                    const cx<T> *s0 = noise_g + size_t(frame) * rowlen + m0, *s1 = s0 + rowlen;
+                    for (int j0 = tid; j0 < fft; j0 += 4 * kOT) {
+                        cx<T> v0[4], v1[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            if (j0 + u * kOT < fft) { v0[u] = load_stream(s0 + j0 + u * kOT); v1[u] = load_stream(s1 + j0 + u * kOT); }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            if (j0 + u * kOT < fft)
+                                Y[j0 + u * kOT] = make_float4(sigma * v0[u].re, sigma * v1[u].re, sigma * v0[u].im, sigma * v1[u].im);
+                    }
+                }
+            }
+            __syncthreads();
+
+            // ---------------- A: map + scatter (lanes = frames)
+            float4 *in = in_w ? W : body;
+            float4 *other = in_w ? body : W;
+            for (int k = tid; k < fft; k += kOT) {
+                const int q = pos_of(k, fft, p.used, p.half);
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (q >= 0) {
+                    const cx<T> s0 = map_symbol<T>(m, tab, dsym[q]);
+                    const cx<T> s1 = map_symbol<T>(m, tab, dsym[p.used + q]);
+                    v = make_float4(tx_scale * s0.re, tx_scale * s1.re, tx_scale * s0.im, tx_scale * s1.im);
+                }
+                in[k] = v;
+            }
+            // ---------------- C: ray setup, items (tap, frame lane)
+            for (int it0 = 0; it0 < n_items; it0 += kOT / G) {
+                const int it = it0 + tid / G;
+                const bool act = it < n_items;
+                const int l = act ? it >> 1 : 0, ln = it & 1;
+                const T amp = T(p.amp[l]);
+                cx<T> a0 = {0.f, 0.f}, a1 = a0, a2 = a0, a3 = a0;
+                const double cseg = double(n_s + cp - p.delays[l]) + 0.5 * double(fft - 1);
+                if (act) {
+                    const T *pphi = ph_phi + ln * p.P4 + l + sub * ostride;
+                    const T *ppsi = ph_psi + ln * p.P4 + l + sub * ostride;
+                    for (int o = sub; o < p.L; o += G, pphi += G * ostride, ppsi += G * ostride) {
+                        const double cphi = p.cos_f32 ? double(cosf(*pphi)) : cos(double(*pphi));
+                        const double dl = wts * cphi;
+                        T sn, cs;
+                        cis_phase<T>(fma(dl, cseg, fma(wt0, cphi, double(*ppsi))), &sn, &cs);
+                        const cx<T> e = {amp * cs, amp * sn};
+                        const T d1 = T(dl), d2 = -0.5f * d1 * d1, d3 = (-1.0f / 3.0f) * d1 * d2;
+                        a0.re += e.re;        a0.im += e.im;
+                        a1.re -= d1 * e.im;   a1.im += d1 * e.re;
+                        a2.re += d2 * e.re;   a2.im += d2 * e.im;
+                        a3.re += d3 * e.im;   a3.im -= d3 * e.re;
+                    }
+                }
+                for (int o = G >> 1; o > 0; o >>= 1) {
+                    a0.re += __shfl_xor_sync(0xffffffffu, a0.re, o); a0.im += __shfl_xor_sync(0xffffffffu, a0.im, o);
+                    a1.re += __shfl_xor_sync(0xffffffffu, a1.re, o); a1.im += __shfl_xor_sync(0xffffffffu, a1.im, o);
+                    a2.re += __shfl_xor_sync(0xffffffffu, a2.re, o); a2.im += __shfl_xor_sync(0xffffffffu, a2.im, o);
+                    a3.re += __shfl_xor_sync(0xffffffffu, a3.re, o); a3.im += __shfl_xor_sync(0xffffffffu, a3.im, o);
+                }
+                if (act && sub == 0) {
+                    if (p.porder != 3) a3 = {0.f, 0.f};
+                    T *cq = reinterpret_cast<T *>(coef) + (l * 4) * 4 + ln;     // [tap][order][re|im][lane]
+                    cq[0] = a0.re; cq[2] = a0.im; cq[4] = a1.re; cq[6] = a1.im;
+                    cq[8] = a2.re; cq[10] = a2.im; cq[12] = a3.re; cq[14] = a3.im;
+                    const T m1 = T(p.mu[0][l]), m2 = T(p.mu[1][l]), m3 = T(p.mu[2][l]);
+                    T *gq = reinterpret_cast<T *>(gbar) + l * 4 + ln;
+                    gq[0] = a0.re + m1 * a1.re + m2 * a2.re + m3 * a3.re;
+                    gq[2] = a0.im + m1 * a1.im + m2 * a2.im + m3 * a3.im;
+                }
+            }
+            // ---------------- B: paired IFFT, cyclic prefix, ISI tail
+            fft_stockham_pair<true>(in, other, tw, fft, p.lg);
+            if constexpr (!FUSED) {                   // ray setup done: the phase buffers are free
+                if (pf && pr + gridDim.x < n_pairs) prefetch(2 * (pr + gridDim.x));
+                cp_async_commit();
+            }
+            for (int i = tid; i < cp; i += kOT) E2[mem + i] = body[fft - cp + i];
+            for (int i = tid; i < mem; i += kOT)
+                E2[i] = (s > 0) ? tails[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+            __syncthreads();
+
+            // ---------------- D: FIR, lane-wise: y += g(tau) * x with all four partial products packed
+            {
+                const float tau0 = float(tid) - 0.5f * float(fft - 1);
+                const float4 *xb = E2 + mem + cp + tid;
+                for (int jo0 = 0; jo0 < fft; jo0 += kOT * kJBC) {
+                    u64 aRR[kJBC], aII[kJBC], aRI[kJBC], aIR[kJBC], tt2[kJBC];
+#pragma unroll
+                    for (int jb = 0; jb < kJBC; ++jb) {
+                        const float tau = tau0 + float(jo0 + jb * kOT);
+                        tt2[jb] = pk2(tau, tau);
+                        aRR[jb] = aII[jb] = aRI[jb] = aIR[jb] = 0ull;
+                    }
+#pragma unroll 3
+                    for (int l = 0; l < p.n_taps; ++l) {
+                        const float4 *xl = xb + (jo0 - p.delays[l]);
+                        u64 cR[4], cI[4];
+#pragma unroll
+                        for (int o = 0; o < 4; ++o) {
+                            const ulonglong2 c = reinterpret_cast<const ulonglong2 *>(coef)[l * 4 + o];
+                            cR[o] = c.x; cI[o] = c.y;
+                        }
+#pragma unroll
+                        for (int jb = 0; jb < kJBC; ++jb) {
+                            const float4 x = xl[jb * kOT];
+                            const u64 xR = pk2(x.x, x.y), xI = pk2(x.z, x.w);
+                            u64 gR = o3 ? fma2(cR[3], tt2[jb], cR[2]) : cR[2];
+                            u64 gI = o3 ? fma2(cI[3], tt2[jb], cI[2]) : cI[2];
+                            gR = fma2(gR, tt2[jb], cR[1]);
+                            gI = fma2(gI, tt2[jb], cI[1]);
+                            gR = fma2(gR, tt2[jb], cR[0]);
+                            gI = fma2(gI, tt2[jb], cI[0]);
+                            aRR[jb] = fma2(gR, xR, aRR[jb]);
+                            aII[jb] = fma2(gI, xI, aII[jb]);
+                            aRI[jb] = fma2(gR, xI, aRI[jb]);
+                            aIR[jb] = fma2(gI, xR, aIR[jb]);
+                        }
+                    }
+                    if (!FUSED && apipe) {
+                        // raw noise rows (frame A | frame B) have landed in Y: y = sigma * noise + FIR
+                        cp_async_wait<1>();
+                        __syncthreads();
+                        cx<T> n0[kJBC], n1[kJBC];
+                        const cx<T> *raw = reinterpret_cast<const cx<T> *>(Y);
+#pragma unroll
+                        for (int jb = 0; jb < kJBC; ++jb) { n0[jb] = raw[tid + jb * kOT]; n1[jb] = raw[fft + tid + jb * kOT]; }
+                        __syncthreads();
+                        const u64 sg = pk2(sigma, sigma);
+#pragma unroll
+                        for (int jb = 0; jb < kJBC; ++jb) {
+                            ps y;                     // rounded product then sum: bit-identical to the fused-RNG path
+                            y.re = add2(mul2(pk2(n0[jb].re, n1[jb].re), sg), sub2(aRR[jb], aII[jb]));
+                            y.im = add2(mul2(pk2(n0[jb].im, n1[jb].im), sg), add2(aRI[jb], aIR[jb]));
+                            st_ps(Y + tid + jb * kOT, y);
+                        }
+                    } else {
+#pragma unroll
+                        for (int jb = 0; jb < kJBC; ++jb) {
+                            const int j = tid + jo0 + jb * kOT;
+                            ps y = ld_ps(Y + j);
+                            y.re = add2(y.re, sub2(aRR[jb], aII[jb]));
+                            y.im = add2(y.im, add2(aRI[jb], aIR[jb]));
+                            st_ps(Y + j, y);
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            if (p.n_sym > 1) {
+                for (int i = tid; i < mem; i += kOT) tails[i] = E2[S + i];
+                __syncthreads();
+            }
+
+            // ---------------- F: paired FFT of both frames
+            {
+                float4 *res = fft_stockham_pair<false>(Y, W, tw, fft, p.lg);
+                if (res != Y) { W = Y; Y = res; }
+            }
+
+            // ---------------- G: H_k (both frames packed), one-tap equaliser, demap, count
+            const int kstride = fft >> 2;
+            for (int k0 = tid; k0 < kstride; k0 += kOT) {
+                ps Sc[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) Sc[c] = {0ull, 0ull};
+                for (int l = 0; l < p.n_taps; ++l) {
+                    const int d = p.delays[l];
+                    const cx<T> w = tw[(k0 * d) & (fft - 1)];
+                    const ps g = {gbar[l * 2], gbar[l * 2 + 1]};
+                    const ps pr2 = mul_w(g, w.re, w.im);
+                    switch (d & 3) {
+                        case 0: Sc[0] = Sc[0] + pr2; break;
+                        case 1: Sc[1] = Sc[1] + pr2; break;
+                        case 2: Sc[2] = Sc[2] + pr2; break;
+                        default: Sc[3] = Sc[3] + pr2; break;
+                    }
+                }
+                ps Hk[4];
+                {
+                    const ps a0 = Sc[0] + Sc[2], a1 = Sc[0] - Sc[2], a2 = Sc[1] + Sc[3], a3 = Sc[1] - Sc[3];
+                    Hk[0] = a0 + a2;
+                    Hk[1] = {add2(a1.re, a3.im), sub2(a1.im, a3.re)};     // a1 - j a3
+                    Hk[2] = a0 - a2;
+                    Hk[3] = {sub2(a1.re, a3.im), add2(a1.im, a3.re)};     // a1 + j a3
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int k = k0 + u * kstride;
+                    const int q = pos_of(k, fft, p.used, p.half);
+                    if (q < 0) continue;
+                    const float4 yv = Y[k];
+                    float hr0, hr1, hi0, hi1;
+                    upk2(Hk[u].re, hr0, hr1);
+                    upk2(Hk[u].im, hi0, hi1);
+#pragma unroll
+                    for (int ln = 0; ln < 2; ++ln) {
+                        const cx<T> y = ln ? mk<T>(rx_scale * yv.y, rx_scale * yv.w) : mk<T>(rx_scale * yv.x, rx_scale * yv.z);
+                        const cx<T> H = ln ? mk<T>(hr1, hi1) : mk<T>(hr0, hi0);
+                        const cx<T> z = cdiv(y, H);
+                        const int a = dsym[ln * p.used + q];
+                        const int e = demap_symbol<T>(m, tab, z);
+                        sym_err += (e != a);
+                        bit_err += __popc(e ^ a);
+                        const size_t o = size_t(frame + ln) * p.n_data + size_t(s * p.used + q);
+                        if (idx_hat) idx_hat[o] = uint8_t(e);
+                        if (eq_out) eq_out[o] = z;
+                    }
+                }
+            }
+            __syncthreads();
+        }   // OFDM symbols
+    }       // frame pairs
+    flush_counters(sym_err, bit_err, counters);
+    if (blockIdx.x == 0 && tid == 0) {
+        atomicAdd(&counters[2], (unsigned long long)n_pairs * 2 * p.n_data);
+        atomicAdd(&counters[3], (unsigned long long)n_pairs * 2 * p.n_data * m.bits);
+    }
+}
+
+inline size_t ofdm_tdl_fpair_smem(const OfdmP &p, int M) {
+    auto al = [](size_t b) { return (b + 15) & ~size_t(15); };
+    size_t s = 0;
+    s += al(sizeof(cx<float>) * p.fft);
+    s += al(sizeof(float4) * (p.mem + p.S));
+    s += al(sizeof(float4) * 2 * p.fft);
+    s += al(sizeof(u64) * p.n_taps * 2);
+    s += al(p.n_sym > 1 ? sizeof(float4) * p.mem : 0);
+    s += al(sizeof(u64) * p.n_taps * 4 * 2);
+    s += al(sizeof(cx<float>) * M);
+    s += al(size_t(2) * p.used);
+    s += 2 * al(sizeof(float) * 2 * p.P4);
+    return s;
+}
+
+inline bool ofdm_tdl_fpair_ok(const OfdmP &p) {
+    return p.poly && p.nseg == 1 && (p.fft & (kOT * kJBC - 1)) == 0 && p.gbar_poly && !p.no_pair;
+}
+
+}  // namespace b200phy

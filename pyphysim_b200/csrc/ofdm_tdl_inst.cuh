@@ -2,7 +2,7 @@
 // configuration so the (large) kernel instantiations compile in parallel.
 #include <type_traits>
 
-#include "ofdm_tdl_pair.cuh"
+#include "ofdm_tdl_fpair.cuh"
 
 namespace b200phy {
 
@@ -63,6 +63,30 @@ static int launch_pair(const OfdmP &p, const Modem &m, const void *table, uint64
     return check_cuda(cudaGetLastError(), "ofdm_tdl_pair_kernel launch");
 }
 
+template <bool FUSED>
+static int launch_fpair(const OfdmP &p, const Modem &m, const void *table, uint64_t first_unit, int64_t n_pairs,
+                        const uint8_t *idx, const void *phi, const void *psi, const void *noise,
+                        uint8_t *idx_hat, void *eq_out, int64_t *counters, size_t smem, cudaStream_t st) {
+    auto kern = ofdm_tdl_fpair_kernel<FUSED>;
+    int e = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)),
+                       "cudaFuncSetAttribute(ofdm_tdl_fpair_kernel)");
+    if (e) return e;
+    int dev = 0, sms = 148, occ = 1;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    e = check_cuda(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kOT, smem),
+                   "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
+    if (e) return e;
+    if (occ < 1) return -1;
+    long long grid = (long long)sms * occ;
+    if (grid > n_pairs) grid = n_pairs;
+    kern<<<int(grid), kOT, smem, st>>>(p, m, (const cx<float> *)table, first_unit, (long long)n_pairs, idx,
+                                       (const float *)phi, (const float *)psi, (const cx<float> *)noise,
+                                       idx_hat, (cx<float> *)eq_out, (unsigned long long *)counters);
+    count_launch();
+    return check_cuda(cudaGetLastError(), "ofdm_tdl_fpair_kernel launch");
+}
+
 template <typename T, int NR, int NT>
 static int launch_typed(const OfdmP &p, const Modem &m, const void *table, uint64_t first_unit,
                         int64_t n_units, const uint8_t *idx, const void *phi, const void *psi,
@@ -71,6 +95,32 @@ static int launch_typed(const OfdmP &p, const Modem &m, const void *table, uint6
     int dev = 0, max_smem = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if constexpr (std::is_same<T, float>::value && NR == 1 && NT == 1) {
+        // SISO: two frames per CTA on the two lanes of the packed FP32 pipe; an odd last frame goes generic
+        if (ofdm_tdl_fpair_ok(p) && n_units >= 2) {
+            const size_t fs = ofdm_tdl_fpair_smem(p, m.M);
+            if (fs <= size_t(max_smem)) {
+                const int64_t n_pairs = n_units / 2;
+                const int e = idx ? launch_fpair<false>(p, m, table, first_unit, n_pairs, idx, phi, psi, noise, idx_hat, eq_out, counters, fs, st)
+                                  : launch_fpair<true>(p, m, table, first_unit, n_pairs, idx, phi, psi, noise, idx_hat, eq_out, counters, fs, st);
+                if (e > 0) return e;
+                if (e == 0) {
+                    const int64_t done = 2 * n_pairs;
+                    if (done == n_units) return 0;
+                    first_unit += uint64_t(done);
+                    n_units -= done;
+                    if (idx) {
+                        idx += size_t(done) * p.n_data;
+                        phi = (const float *)phi + size_t(done) * p.P;
+                        psi = (const float *)psi + size_t(done) * p.P;
+                        noise = (const cx<float> *)noise + size_t(done) * size_t(p.N + p.mem);
+                    }
+                    if (idx_hat) idx_hat += size_t(done) * p.n_data;
+                    if (eq_out) eq_out = (cx<float> *)eq_out + size_t(done) * p.n_data;
+                }
+            }
+        }
+    }
     if constexpr (std::is_same<T, float>::value && (NR % 2 == 0) && (NT % 2 == 0)) {
         if (ofdm_tdl_pair_ok(p, NR, NT)) {
             const size_t ps = ofdm_tdl_pair_smem(p, m.M, NR, NT);

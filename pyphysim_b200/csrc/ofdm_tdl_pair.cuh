@@ -134,6 +134,36 @@ ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m, const cx<fl
     const double wts = p.w0 * p.Ts1, wt0 = p.w0 * p.t0;
     const bool in_w = p.ifft_in_w != 0;
 
+    // Stream mode input pipeline (LDGSTS).  `pf`: the phases and data symbols of the NEXT frame are copied
+    // into shared memory while this frame is in the FIR (one OFDM symbol per frame only: then the phase
+    // buffers are free after the ray setup).  `apipe`: the raw noise rows of an rx pair are copied into that
+    // pair's (still unused) accumulator buffer at frame start and merged in the FIR epilogue.
+    // The data symbols of the next frame (<= 8 B per thread) wait in two registers instead.
+    const bool pf = !FUSED && p.n_sym == 1 && (p.n_data & 7) == 0 && p.n_data <= 8 * kOT &&
+                    (reinterpret_cast<uintptr_t>(idx_g) & 7) == 0;
+    const bool pf16 = pf && (p.P & 3) == 0 && aligned16(phi_g) && aligned16(psi_g);
+    const bool apipe = !FUSED && fft == kOT * kJBC;
+    uint2 idx_pre = make_uint2(0u, 0u);
+    auto prefetch = [&](long long f) {
+        const T *gp = phi_g + size_t(f) * p.P, *gq = psi_g + size_t(f) * p.P;
+        if (pf16) {
+            for (int i = tid; i < (p.P >> 2); i += kOT) {
+                cp_async<16>(ph_phi + 4 * i, gp + 4 * i);
+                cp_async<16>(ph_psi + 4 * i, gq + 4 * i);
+            }
+        } else {
+            for (int i = tid; i < p.P; i += kOT) {
+                cp_async<4>(ph_phi + i, gp + i);
+                cp_async<4>(ph_psi + i, gq + i);
+            }
+        }
+        if (tid < (p.n_data >> 3)) idx_pre = __ldg(reinterpret_cast<const uint2 *>(idx_g + size_t(f) * p.n_data) + tid);
+    };
+    if constexpr (!FUSED) {
+        if (pf && blockIdx.x < n_units) prefetch(blockIdx.x);
+        cp_async_commit();
+    }
+
     for (long long frame = blockIdx.x; frame < n_units; frame += gridDim.x) {
         const uint64_t unit = first_unit + uint64_t(frame);
         float4 *Yp[NP];
@@ -152,6 +182,9 @@ ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m, const cx<fl
                     ph_psi[4 * b + l] = phase_from_word<T>(lane_of(b2, l));
                 }
             }
+        } else if (pf) {
+            cp_async_wait<0>();                      // prefetched during the previous frame (visible after the barrier below)
+            if (tid < (p.n_data >> 3)) reinterpret_cast<uint2 *>(dsym)[tid] = idx_pre;
         } else {
             const T *gp = phi_g + size_t(frame) * p.P, *gq = psi_g + size_t(frame) * p.P;
             for (int i0 = tid; i0 < p.P; i0 += 4 * kOT) {
@@ -180,7 +213,7 @@ ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m, const cx<fl
                             if (w >= 0 && w < cnt) dsym[w] = uint8_t(lane_of(blk, l) >> (32 - m.bits));
                         }
                     }
-                } else {
+                } else if (!pf) {
                     const uint8_t *src = idx_g + frame * p.n_data + w0;
                     if ((cnt & 3) == 0 && ((frame * p.n_data + w0) & 3) == 0) {
                         const uint32_t *s4 = reinterpret_cast<const uint32_t *>(src);
@@ -201,6 +234,20 @@ ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m, const cx<fl
                         if (j >= 0 && j < fft) { const cx<T> c = sigma * cnormal<T>(blk.x, blk.y); yr[4 * j] = c.re; yr[4 * j + 2] = c.im; }
                         if (j + 1 >= 0 && j + 1 < fft) { const cx<T> c = sigma * cnormal<T>(blk.z, blk.w); yr[4 * j + 4] = c.re; yr[4 * j + 6] = c.im; }
                     }
+                } else if (apipe) {
+                    // raw rows (rx 2q | rx 2q+1) into the pair buffer; merged into pair layout after the FIR
+                    const size_t rowlen = size_t(p.N + mem);
+#pragma unroll
+                    for (int q = 0; q < NP; ++q) {
+                        const cx<T> *s0 = noise_g + (size_t(frame) * NR + 2 * q) * rowlen + m0, *s1 = s0 + rowlen;
+                        cx<T> *raw = reinterpret_cast<cx<T> *>(Yp[q]);
+#pragma unroll
+                        for (int jb = 0; jb < kJBC; ++jb) {
+                            cp_async<8>(raw + tid + jb * kOT, s0 + tid + jb * kOT);
+                            cp_async<8>(raw + fft + tid + jb * kOT, s1 + tid + jb * kOT);
+                        }
+                    }
+                    cp_async_commit();
                 } else {
                     const size_t rowlen = size_t(p.N + mem);
 #pragma unroll
@@ -280,6 +327,12 @@ ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m, const cx<fl
                 }
                 // ---------------- B: paired IFFT (ends in E2.body), cyclic prefix, ISI tail
                 fft_stockham_pair<true>(in, other, tw, fft, p.lg);
+                if constexpr (!FUSED) {
+                    if (tp == TP - 1) {              // last ray setup done: the phase buffers are free
+                        if (pf && frame + gridDim.x < n_units) prefetch(frame + gridDim.x);
+                        cp_async_commit();
+                    }
+                }
                 for (int i = tid; i < cp; i += kOT) E2[mem + i] = body[fft - cp + i];
                 for (int i = tid; i < mem; i += kOT)
                     E2[i] = (s > 0) ? tails[tp * mem + i] : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -337,15 +390,42 @@ ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m, const cx<fl
                                 }
                             }
                         }
+                        if (!FUSED && apipe && tp == 0) {
+                            // the raw noise rows have landed in Yp[q]: y = sigma * noise + FIR, re-laid as pairs
+                            if (TP == 1) cp_async_wait<1>(); else cp_async_wait<0>();
+                            __syncthreads();
+                            cx<T> n0[kJBC][NP], n1[kJBC][NP];
 #pragma unroll
-                        for (int jb = 0; jb < kJBC; ++jb) {
-                            const int j = tid + jo0 + jb * kOT;
+                            for (int jb = 0; jb < kJBC; ++jb)
 #pragma unroll
-                            for (int q = 0; q < NP; ++q) {
-                                ps y = ld_ps(Yp[q] + j);
-                                y.re = add2(y.re, aRe[jb][q]);
-                                y.im = add2(y.im, aIm[jb][q]);
-                                st_ps(Yp[q] + j, y);
+                                for (int q = 0; q < NP; ++q) {
+                                    const cx<T> *raw = reinterpret_cast<const cx<T> *>(Yp[q]);
+                                    n0[jb][q] = raw[tid + jb * kOT];
+                                    n1[jb][q] = raw[fft + tid + jb * kOT];
+                                }
+                            __syncthreads();
+                            const u64 sg = pk2(sigma, sigma);
+#pragma unroll
+                            for (int jb = 0; jb < kJBC; ++jb)
+#pragma unroll
+                                for (int q = 0; q < NP; ++q) {
+                                    ps y;
+                                    // rounded product then sum: bit-identical to the fused-RNG path
+                                    y.re = add2(mul2(pk2(n0[jb][q].re, n1[jb][q].re), sg), aRe[jb][q]);
+                                    y.im = add2(mul2(pk2(n0[jb][q].im, n1[jb][q].im), sg), aIm[jb][q]);
+                                    st_ps(Yp[q] + tid + jb * kOT, y);
+                                }
+                        } else {
+#pragma unroll
+                            for (int jb = 0; jb < kJBC; ++jb) {
+                                const int j = tid + jo0 + jb * kOT;
+#pragma unroll
+                                for (int q = 0; q < NP; ++q) {
+                                    ps y = ld_ps(Yp[q] + j);
+                                    y.re = add2(y.re, aRe[jb][q]);
+                                    y.im = add2(y.im, aIm[jb][q]);
+                                    st_ps(Yp[q] + j, y);
+                                }
                             }
                         }
                     }

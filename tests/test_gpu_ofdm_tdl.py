@@ -186,6 +186,31 @@ def test_pair_kernel_vs_generic_kernel(ant, fft, cp, nsym):
     run_stream_vs_oracle(cfg, pair, np.arange(300, 301), exact=False, rel=1e-4, eps=2e-3)
 
 
+@pytest.mark.parametrize('mod,M,fft,cp,nsym,n', [('qam', 64, 1024, 72, 1, 13), ('psk', 8, 2048, 144, 2, 6),
+                                                 ('qam', 16, 1024, 0, 3, 2)])
+def test_frame_pair_kernel_vs_generic_kernel(mod, M, fft, cp, nsym, n):
+    """SISO: the two-frames-per-CTA FFMA2 kernel (odd batch: the last frame runs on the generic kernel)
+    against the generic kernel on the same draws, its fused mode against its stream mode, and the
+    oracle on the first two frames."""
+    import torch
+    from pyphysim_b200 import links
+    cfg, pair = make_pair(mod, M, fft, cp, fft, n_sym=nsym, dtype='f32', snr_dB=24.0)
+    gen = links.OfdmTdlLink(pair.modulator, fft, cp, fft, num_ofdm_symbols=nsym, Nr=1, Nt=1,
+                            tap_powers_linear=cfg.tap_powers, tap_delays=cfg.delays, Fd=10.0, Ts=cfg.Ts, L=20,
+                            t0=cfg.t0, noise_var=cfg.noise_var, dtype='f32', seed=SEED, use_pair_kernel=False)
+    draws = pair.draw(500, n)
+    c_p, hat_p, eq_p = pair.run(n, first_unit=500, draws=draws, want_idx=True, want_eq=True)
+    c_g, hat_g, eq_g = gen.run(n, first_unit=500, draws=draws, want_idx=True, want_eq=True)
+    assert_samples_close(_t(eq_p), _t(eq_g), 2e-5, 'frame-pair vs generic')
+    nbad = assert_decisions(_t(hat_p), _t(hat_g), cfg.modem, _t(eq_g).astype(complex), exact=False, eps=2e-3)
+    assert abs(int(c_p[0]) - int(c_g[0])) <= nbad and c_p[2] == c_g[2] == n * nsym * fft
+    c_f, hat_f = pair.run(n, first_unit=500, want_idx=True)
+    assert np.array_equal(c_f, c_p) and torch.equal(hat_f, hat_p)
+    c_n = pair.run(n, first_unit=500)                                        # counters only, no outputs
+    assert np.array_equal(c_n, c_p)
+    run_stream_vs_oracle(cfg, pair, np.arange(500, 502), exact=False, rel=1e-4, eps=2e-3)
+
+
 def test_full_size_properties():
     """At BASELINE sizes: noiseless frames decode without error; error rate grows with noise;
     repeatable; totals exact."""
