@@ -253,31 +253,35 @@ ofdm_tdl_fpair_kernel(const __grid_constant__ OfdmP p, const Modem m, const cx<f
                         tt2[jb] = pk2(tau, tau);
                         aRR[jb] = aII[jb] = aRI[jb] = aIR[jb] = 0ull;
                     }
-#pragma unroll 3
-                    for (int l = 0; l < p.n_taps; ++l) {
-                        const float4 *xl = xb + (jo0 - p.delays[l]);
-                        u64 cR[4], cI[4];
+                    auto taps = [&](auto order3) {          // specialised on the polynomial order
+                        constexpr int NO = decltype(order3)::value ? 4 : 3;
+#pragma unroll 2
+                        for (int l = 0; l < p.n_taps; ++l) {
+                            const float4 *xl = xb + (jo0 - p.delays[l]);
+                            u64 cR[NO], cI[NO];
 #pragma unroll
-                        for (int o = 0; o < 4; ++o) {
-                            const ulonglong2 c = reinterpret_cast<const ulonglong2 *>(coef)[l * 4 + o];
-                            cR[o] = c.x; cI[o] = c.y;
-                        }
+                            for (int o = 0; o < NO; ++o) {
+                                const ulonglong2 c = reinterpret_cast<const ulonglong2 *>(coef)[l * 4 + o];
+                                cR[o] = c.x; cI[o] = c.y;
+                            }
 #pragma unroll
-                        for (int jb = 0; jb < kJBC; ++jb) {
-                            const float4 x = xl[jb * kOT];
-                            const u64 xR = pk2(x.x, x.y), xI = pk2(x.z, x.w);
-                            u64 gR = o3 ? fma2(cR[3], tt2[jb], cR[2]) : cR[2];
-                            u64 gI = o3 ? fma2(cI[3], tt2[jb], cI[2]) : cI[2];
-                            gR = fma2(gR, tt2[jb], cR[1]);
-                            gI = fma2(gI, tt2[jb], cI[1]);
-                            gR = fma2(gR, tt2[jb], cR[0]);
-                            gI = fma2(gI, tt2[jb], cI[0]);
-                            aRR[jb] = fma2(gR, xR, aRR[jb]);
-                            aII[jb] = fma2(gI, xI, aII[jb]);
-                            aRI[jb] = fma2(gR, xI, aRI[jb]);
-                            aIR[jb] = fma2(gI, xR, aIR[jb]);
+                            for (int jb = 0; jb < kJBC; ++jb) {
+                                const float4 x = xl[jb * kOT];
+                                const u64 xR = pk2(x.x, x.y), xI = pk2(x.z, x.w);
+                                u64 gR = cR[NO - 1], gI = cI[NO - 1];
+#pragma unroll
+                                for (int o = NO - 2; o >= 0; --o) {
+                                    gR = fma2(gR, tt2[jb], cR[o]);
+                                    gI = fma2(gI, tt2[jb], cI[o]);
+                                }
+                                aRR[jb] = fma2(gR, xR, aRR[jb]);
+                                aII[jb] = fma2(gI, xI, aII[jb]);
+                                aRI[jb] = fma2(gR, xI, aRI[jb]);
+                                aIR[jb] = fma2(gI, xR, aIR[jb]);
+                            }
                         }
-                    }
+                    };
+                    if (o3) taps(std::true_type{}); else taps(std::false_type{});
                     if (!FUSED && apipe) {
                         // raw noise rows (frame A | frame B) have landed in Y: y = sigma * noise + FIR
                         cp_async_wait<1>();

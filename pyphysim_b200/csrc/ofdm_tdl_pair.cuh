@@ -11,6 +11,8 @@
 // Semantics, draws, restatements and error bounds are exactly those of ofdm_tdl.cuh (same OfdmP);
 // tests run both kernels against the oracle and against each other.
 #pragma once
+#include <type_traits>
+
 #include "ofdm_tdl.cuh"
 
 namespace b200phy {
@@ -351,45 +353,49 @@ ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m, const cx<fl
 #pragma unroll
                             for (int q = 0; q < NP; ++q) { aRe[jb][q] = 0ull; aIm[jb][q] = 0ull; }
                         }
-                        for (int l = 0; l < p.n_taps; ++l) {
-                            const float4 *xl = xb + (jo0 - p.delays[l]);
-                            float4 x4[kJBC];
+                        // the whole tap loop is specialised on the polynomial order (one uniform branch per
+                        // block of outputs instead of one per tap, which cost a register shuffle at every join)
+                        auto taps = [&](auto order3) {
+                            constexpr bool O3 = decltype(order3)::value;
+                            constexpr int NO = O3 ? 4 : 3;
+                            for (int l = 0; l < p.n_taps; ++l) {
+                                const float4 *xl = xb + (jo0 - p.delays[l]);
+                                float4 x4[kJBC];
 #pragma unroll
-                            for (int jb = 0; jb < kJBC; ++jb) x4[jb] = xl[jb * kOT];
+                                for (int jb = 0; jb < kJBC; ++jb) x4[jb] = xl[jb * kOT];
 #pragma unroll
-                            for (int tt = 0; tt < 2; ++tt) {
-                                u64 cR[NP][4], cI[NP][4];
+                                for (int tt = 0; tt < 2; ++tt) {
+                                    u64 cR[NP][NO], cI[NP][NO];
 #pragma unroll
-                                for (int q = 0; q < NP; ++q)
+                                    for (int q = 0; q < NP; ++q)
 #pragma unroll
-                                    for (int o = 0; o < 4; ++o) {
-                                        cR[q][o] = coef[(((l * NP + q) * 2 + tt) * 4 + o) * 2];
-                                        cI[q][o] = coef[(((l * NP + q) * 2 + tt) * 4 + o) * 2 + 1];
-                                    }
-#pragma unroll
-                                for (int jb = 0; jb < kJBC; ++jb) {
-                                    const u64 tt2 = pk2(tauv[jb], tauv[jb]);
-                                    const float xr = tt ? x4[jb].y : x4[jb].x, xi = tt ? x4[jb].w : x4[jb].z;
-                                    const u64 xrr = pk2(xr, xr), xii = pk2(xi, xi), nxii = pk2(-xi, -xi);
-#pragma unroll
-                                    for (int q = 0; q < NP; ++q) {
-                                        u64 gR, gI;
-                                        if (p.porder == 3) {
-                                            gR = fma2(cR[q][3], tt2, cR[q][2]); gI = fma2(cI[q][3], tt2, cI[q][2]);
-                                            gR = fma2(gR, tt2, cR[q][1]);       gI = fma2(gI, tt2, cI[q][1]);
-                                        } else {
-                                            gR = fma2(cR[q][2], tt2, cR[q][1]); gI = fma2(cI[q][2], tt2, cI[q][1]);
+                                        for (int o = 0; o < NO; ++o) {
+                                            const ulonglong2 c = reinterpret_cast<const ulonglong2 *>(coef)[((l * NP + q) * 2 + tt) * 4 + o];
+                                            cR[q][o] = c.x; cI[q][o] = c.y;
                                         }
-                                        gR = fma2(gR, tt2, cR[q][0]);
-                                        gI = fma2(gI, tt2, cI[q][0]);
-                                        aRe[jb][q] = fma2(gR, xrr, aRe[jb][q]);
-                                        aRe[jb][q] = fma2(gI, nxii, aRe[jb][q]);
-                                        aIm[jb][q] = fma2(gR, xii, aIm[jb][q]);
-                                        aIm[jb][q] = fma2(gI, xrr, aIm[jb][q]);
+#pragma unroll
+                                    for (int jb = 0; jb < kJBC; ++jb) {
+                                        const u64 tt2 = pk2(tauv[jb], tauv[jb]);
+                                        const float xr = tt ? x4[jb].y : x4[jb].x, xi = tt ? x4[jb].w : x4[jb].z;
+                                        const u64 xrr = pk2(xr, xr), xii = pk2(xi, xi), nxii = pk2(-xi, -xi);
+#pragma unroll
+                                        for (int q = 0; q < NP; ++q) {
+                                            u64 gR = cR[q][NO - 1], gI = cI[q][NO - 1];
+#pragma unroll
+                                            for (int o = NO - 2; o >= 0; --o) {
+                                                gR = fma2(gR, tt2, cR[q][o]);
+                                                gI = fma2(gI, tt2, cI[q][o]);
+                                            }
+                                            aRe[jb][q] = fma2(gR, xrr, aRe[jb][q]);
+                                            aRe[jb][q] = fma2(gI, nxii, aRe[jb][q]);
+                                            aIm[jb][q] = fma2(gR, xii, aIm[jb][q]);
+                                            aIm[jb][q] = fma2(gI, xrr, aIm[jb][q]);
+                                        }
                                     }
                                 }
                             }
-                        }
+                        };
+                        if (p.porder == 3) taps(std::true_type{}); else taps(std::false_type{});
                         if (!FUSED && apipe && tp == 0) {
                             // the raw noise rows have landed in Yp[q]: y = sigma * noise + FIR, re-laid as pairs
                             if (TP == 1) cp_async_wait<1>(); else cp_async_wait<0>();
