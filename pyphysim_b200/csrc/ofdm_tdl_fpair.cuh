@@ -197,7 +197,15 @@ ofdm_tdl_fpair_kernel(const __grid_constant__ OfdmP p, const Modem m, const cx<f
                 const T amp = T(p.amp[l]);
                 cx<T> a0 = {0.f, 0.f}, a1 = a0, a2 = a0, a3 = a0;
                 const double cseg = double(n_s + cp - p.delays[l]) + 0.5 * double(fft - 1);
-                if (act) {
+                if (act && p.cos_f32) {
+                    const T *pphi = ph_phi + ln * p.P4 + l + sub * ostride;
+                    const T *ppsi = ph_psi + ln * p.P4 + l + sub * ostride;
+                    cx<T> a[4] = {a0, a0, a0, a0};
+                    const float eps = float(fma(wts, cseg, wt0)), wtsf = float(wts);
+                    if (o3) ray_moments_f32<true>(a, pphi, ppsi, sub, p.L, G, ostride, eps, wtsf);
+                    else ray_moments_f32<false>(a, pphi, ppsi, sub, p.L, G, ostride, eps, wtsf);
+                    a0 = amp * a[0]; a1 = amp * a[1]; a2 = amp * a[2]; a3 = amp * a[3];
+                } else if (act) {
                     const T *pphi = ph_phi + ln * p.P4 + l + sub * ostride;
                     const T *ppsi = ph_psi + ln * p.P4 + l + sub * ostride;
                     for (int o = sub; o < p.L; o += G, pphi += G * ostride, ppsi += G * ostride) {

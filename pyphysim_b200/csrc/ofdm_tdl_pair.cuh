@@ -90,6 +90,38 @@ __device__ float4 *fft_stockham_pair(float4 *a, float4 *b, const cx<float> *tw, 
     return src;
 }
 
+// Unscaled Taylor moments of one (tap, rx, tx) item's rays about the expansion centre,
+//   a_o = sum_rays cis(theta_ray) (j d_ray)^o / o!,   theta = psi + eps cos(phi),  d = wts cos(phi),
+// entirely in float.  Valid in the slow-fading regime the host flags with OfdmP::cos_f32 (total phase
+// advance |eps| < 0.05 rad, so theta needs no extended precision); phases are drawn in [0, 2 pi).
+template <bool O3>
+__device__ __forceinline__ void ray_moments_f32(cx<float> (&a)[4], const float *pphi, const float *ppsi, int first,
+                                                int L, int step, int stride, float eps, float wts) {
+    // psi / pi as a two-float product (hi + lo of 1/pi), reduced by the nearest even integer before the
+    // small terms are added: the phase reaches sincospif with ~6e-8 half-turn error, like the double path
+    constexpr float kInvPi = 0.31830987334251404f, kInvPiLo = 1.284127663345183e-08f;
+    const float eps_pi = eps * kInvPi;
+#pragma unroll 2
+    for (int o = first; o < L; o += step, pphi += step * stride, ppsi += step * stride) {
+        const float cphi = cospif(*pphi * kInvPi);
+        const float d1 = wts * cphi, d2 = -0.5f * d1 * d1;
+        const float psi = *ppsi, t = psi * kInvPi;
+        float e = fmaf(psi, kInvPi, -t);
+        e = fmaf(psi, kInvPiLo, e);
+        e = fmaf(eps_pi, cphi, e);
+        float sn, cs;
+        sincospif((t - 2.0f * rintf(0.5f * t)) + e, &sn, &cs);
+        a[0].re += cs;                      a[0].im += sn;
+        a[1].re = fmaf(-d1, sn, a[1].re);   a[1].im = fmaf(d1, cs, a[1].im);
+        a[2].re = fmaf(d2, cs, a[2].re);    a[2].im = fmaf(d2, sn, a[2].im);
+        if constexpr (O3) {
+            const float d3 = (-1.0f / 3.0f) * d1 * d2;
+            a[3].re = fmaf(d3, sn, a[3].re);
+            a[3].im = fmaf(-d3, cs, a[3].im);
+        }
+    }
+}
+
 template <bool FUSED, int NR, int NT>
 __global__ void __launch_bounds__(kOT, (NR * NT <= 4) ? 3 : 1)
 ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m, const cx<float> *__restrict__ tab_g,
@@ -294,7 +326,15 @@ ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m, const cx<fl
                     const T amp = T(p.amp[l]);
                     cx<T> a0 = {0.f, 0.f}, a1 = a0, a2 = a0, a3 = a0;
                     const double cseg = double(n_s + cp - p.delays[l]) + 0.5 * double(fft - 1);
-                    if (act) {
+                    if (act && p.cos_f32) {
+                        const T *pphi = ph_phi + ((l * NR + r) * NT + t) + sub * ostride;
+                        const T *ppsi = ph_psi + ((l * NR + r) * NT + t) + sub * ostride;
+                        cx<T> a[4] = {a0, a0, a0, a0};
+                        const float eps = float(fma(wts, cseg, wt0)), wtsf = float(wts);
+                        if (p.porder == 3) ray_moments_f32<true>(a, pphi, ppsi, sub, p.L, G, ostride, eps, wtsf);
+                        else ray_moments_f32<false>(a, pphi, ppsi, sub, p.L, G, ostride, eps, wtsf);
+                        a0 = amp * a[0]; a1 = amp * a[1]; a2 = amp * a[2]; a3 = amp * a[3];
+                    } else if (act) {
                         const T *pphi = ph_phi + ((l * NR + r) * NT + t) + sub * ostride;
                         const T *ppsi = ph_psi + ((l * NR + r) * NT + t) + sub * ostride;
                         for (int o = sub; o < p.L; o += G, pphi += G * ostride, ppsi += G * ostride) {
