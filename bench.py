@@ -70,7 +70,21 @@ class ClockSampler(threading.Thread):
                 break
             parts = [c.strip() for c in line.strip().split(',')]
             if len(parts) >= 7:
-                self.rows.append(parts)
+                self.rows.append(parts + [time.perf_counter()])
+
+    def wait_first(self, timeout=3.0):
+        """Block until nvidia-smi has delivered its first sample (it takes a few hundred ms to start)."""
+        t0 = time.perf_counter()
+        while not self.rows and time.perf_counter() - t0 < timeout and self.is_alive():
+            time.sleep(0.02)
+
+    def begin(self):
+        """Only samples taken after this call (i.e. under load) are summarised."""
+        self.t_begin = time.perf_counter()
+
+    def under_load(self):
+        tb = getattr(self, 't_begin', 0.0)
+        return [r for r in list(self.rows) if r[-1] >= tb]
 
     def stop(self):
         self.stop_flag = True
@@ -80,14 +94,15 @@ class ClockSampler(threading.Thread):
         self.join(timeout=2)
 
     def summary(self):
-        if not self.rows:
+        rows = self.under_load()
+        if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        sm = [float(r[0]) for r in self.rows if r[0].replace('.', '').isdigit()]
-        mx = [float(r[1]) for r in self.rows if r[1].replace('.', '').isdigit()]
+        sm = [float(r[0]) for r in rows if r[0].replace('.', '').isdigit()]
+        mx = [float(r[1]) for r in rows if r[1].replace('.', '').isdigit()]
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith('active') for r in self.rows)]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith('active') for r in rows)]
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.rows)}
+                "reasons": reasons, "samples": len(rows)}
 
 
 # ------------------------------------------------------------------ workload construction
@@ -335,7 +350,9 @@ def main():
         full_step()
     sampler = ClockSampler(local)
     sampler.start()
-    time.sleep(0.15)                                   # let the first samples arrive
+    sampler.wait_first()
+    full_step()                                        # GPU busy again before the sampled window opens
+    sampler.begin()
     l0 = lib.b200phy_launch_count()
     ms_step = timed(full_step, args.steps)
     launches = int(lib.b200phy_launch_count() - l0)
@@ -343,6 +360,12 @@ def main():
     for _ in range(warm):
         fused()
     ms_fused = timed(fused, args.steps)
+    # short workloads end before nvidia-smi's 50 ms period has produced enough samples: keep the SAME
+    # load running (untimed) until there are a few, so the reported clocks are clocks under this load
+    t_ext = time.perf_counter()
+    while len(sampler.under_load()) < 4 and time.perf_counter() - t_ext < 2.0:
+        step()
+        torch.cuda.synchronize()
     sampler.stop()
     final = counters.cpu().numpy().tolist()
 
@@ -360,9 +383,25 @@ def main():
         dt = torch.tensor([(time.perf_counter() - t0) / ke], device='cuda', dtype=torch.float64)
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * Re / float(dt.item()), "unit": "realizations/s",
+        e2e_s = float(dt.item())
+        # the e2e path is PCIe-bound: time a plain pinned H2D copy of the same size on this box beside it
+        probe_h = torch.empty(min(int(h2d), 1 << 29), dtype=torch.uint8, pin_memory=True)
+        probe_d = torch.empty(probe_h.numel(), dtype=torch.uint8, device='cuda')
+        probe_d.copy_(probe_h, non_blocking=True)
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        p0.record()
+        for _ in range(3):
+            probe_d.copy_(probe_h, non_blocking=True)
+        p1.record()
+        torch.cuda.synchronize()
+        h2d_gbs = 3 * probe_h.numel() / (p0.elapsed_time(p1) * 1e-3) / 1e9
+        del probe_h, probe_d
+        e2e = {"value": world * Re / e2e_s, "unit": "realizations/s",
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "units_per_step_per_gpu": Re, "api": "b200phy_link_*_host (pinned host draws, stream mode)"}
+               "units_per_step_per_gpu": Re, "api": "b200phy_link_*_host (pinned host draws, stream mode)",
+               "h2d_gbs_achieved": h2d / e2e_s / 1e9, "h2d_gbs_plain_memcpy": h2d_gbs,
+               "pcie_frac": (h2d / e2e_s / 1e9) / h2d_gbs}
 
     if rank != 0:
         if world > 1:

@@ -138,7 +138,9 @@ int b200phy_link_ofdm_tdl_host(const b200phy_ofdm_tdl_params *p, int modem_kind,
     const size_t P = size_t(p->L) * p->n_taps * p->Nr * p->Nt;
     const size_t nrow = size_t(p->Nr) * (size_t(p->n_sym) * (p->fft + p->cp) + p->delays[p->n_taps - 1]);
     const size_t per_frame = n_data + 2 * P * rsz + nrow * csz;
-    int64_t chunk = int64_t((size_t(256) << 20) / per_frame);       // ~256 MiB of draws per chunk
+    // ~64 MiB of draws per chunk: long enough to run PCIe at full rate and fill the GPU (>= 2000 frames),
+    // short enough that the un-overlapped head (first H2D) and tail (last kernel + D2H) stay small
+    int64_t chunk = int64_t((size_t(64) << 20) / per_frame);
     if (chunk < 1) chunk = 1;
     for (auto &s : g_ctx.slot) B200_CU(cudaMemsetAsync(s.counters, 0, 4 * sizeof(long long), s.st), "memset");
     int ci = 0;

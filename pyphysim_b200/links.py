@@ -125,7 +125,8 @@ class OfdmTdlLink:
         idx = phi = psi = noise = None
         if draws is not None:
             idx, phi, psi, noise = draws
-        hat = torch.empty((n_units, self.n_data), dtype=torch.uint8).pin_memory() if want_idx else None
+        # pinned straight from torch's caching host allocator (no pageable staging copy)
+        hat = torch.empty((n_units, self.n_data), dtype=torch.uint8, pin_memory=True) if want_idx else None
         _lib.check(lib.b200phy_link_ofdm_tdl_host(
             C.byref(self.params), self.modulator._kind, self.modulator.M, tp, first_unit, n_units,
             _lib.ptr(idx), _lib.ptr(phi), _lib.ptr(psi), _lib.ptr(noise), _lib.ptr(hat),
@@ -165,7 +166,7 @@ def link_siso_flat_host(modulator, noise_var, n_units, *, rayleigh=True, seed=SE
     idx = h = noise = None
     if draws is not None:
         idx, h, noise = draws
-    hat = torch.empty(n_units, dtype=torch.uint8).pin_memory() if want_idx else None
+    hat = torch.empty(n_units, dtype=torch.uint8, pin_memory=True) if want_idx else None
     _lib.check(lib.b200phy_link_siso_flat_host(dt, modulator._kind, modulator.M, tp, int(bool(rayleigh)),
                                                float(noise_var), seed, first_unit, n_units,
                                                _lib.ptr(idx), _lib.ptr(h), _lib.ptr(noise),
