@@ -39,6 +39,9 @@ WORKLOADS = {
                                            Nt=4, snr_dB=30.0, units=20000),
     'c2_qam64_flat_rayleigh': dict(kind='siso_flat', M=64, snr_dB=15.0, units=100000000),
     'c4_qpsk_alamouti2x2': dict(kind='alamouti', M=4, Nr=2, S=2, snr_dB=10.0, units=20000000),
+    # channel-dependent precoding, one 4x4 SVD (+ GMD) per realization, 16 symbol vectors
+    'n3_qam16_svd4x4': dict(kind='precoded', scheme='svd', M=16, Nr=4, Nt=4, S=16, snr_dB=20.0, units=4000000),
+    'n3_qam16_gmd4x4': dict(kind='precoded', scheme='gmd', M=16, Nr=4, Nt=4, S=16, snr_dB=20.0, units=4000000),
 }
 DEFAULT = 'ofdm1024_qam64_mimo2x2_tdl'
 SEED = 0x5EEDB200
@@ -150,6 +153,14 @@ def oracle_frame_runner(w):
                 tot += OL.counters(idx, hat, om.bits)
             return tot
         return run
+    if w['kind'] == 'precoded':
+        om = OL.Modem('qam', w['M'])
+
+        def run(units):
+            idx, H, n = OL.draws_flat_mimo(SEED, units, om.bits, w['Nr'], w['Nt'], w['S'], w['S'] * w['Nt'])
+            hat, _ = OL.precoded_flat(om, w['scheme'], idx, H, n, 1.0 / dB2Linear(w['snr_dB']))
+            return OL.counters(idx, hat, om.bits)
+        return run
     om = OL.Modem('psk', 4, np.pi / 4)
 
     def run(units):
@@ -171,7 +182,7 @@ def _cpu_worker(args):
 def cpu_sample_size(w):
     """Units for the single-core cpu_baseline leg: about 10-20 s of NumPy work."""
     return {'ofdm': 256 if w.get('Nr', 1) * w.get('Nt', 1) <= 4 else 32, 'siso_flat': 4000000,
-            'alamouti': 300000}[w['kind']]
+            'alamouti': 300000, 'precoded': 60000}[w['kind']]
 
 
 def time_cpu(wname, cores, units_per_core):
@@ -313,6 +324,17 @@ def main():
         h2d = sum(t.numel() * t.element_size() for t in host_draws)
         d2h = Re + 32
         sym_per_unit = 1
+    elif w['kind'] == 'precoded':
+        mod = QAM(w['M'])
+        nv = 1.0 / dB2Linear(w['snr_dB'])
+        S, Nr, Nt, sch = w['S'], w['Nr'], w['Nt'], w['scheme']
+        bytes_per_unit = S * Nt + Nr * Nt * 8 + Nr * S * 8 + S * Nt          # idx + H + noise in, idx_hat out
+        draws = links.draw_flat_mimo(mod, R, Nr=Nr, Nt=Nt, num_symbols=S, n_data=S * Nt, seed=SEED, first_unit=first)
+        kw = dict(scheme=sch, Nr=Nr, Nt=Nt, num_symbols=S)
+        step = lambda: links.link_precoded(mod, nv, R, draws=draws, counters=counters, want_idx=True, **kw)  # noqa: E731
+        fused = lambda: links.link_precoded(mod, nv, R, seed=SEED, first_unit=first, counters=counters, **kw)  # noqa: E731
+        e2e_call, Re, h2d, d2h = None, 0, 0, 0
+        sym_per_unit = S * Nt
     else:
         mod = QPSK()
         nv = 1.0 / dB2Linear(w['snr_dB'])
@@ -430,7 +452,9 @@ def main():
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s",
                      "bytes_per_unit": bytes_per_unit, "kernel_ms": ms_kernel,
                      "note": ("OFDM/TDL frames are instruction-issue bound, not HBM bound (see `issue`, DESIGN.md, "
-                              "profiles/)") if w['kind'] == 'ofdm' else "HBM-bound elementwise link"},
+                              "profiles/)") if w['kind'] == 'ofdm' else
+                             ("bound by the per-realization double-precision Jacobi SVD (FP64 pipe), not HBM"
+                              if w['kind'] == 'precoded' else "HBM-bound elementwise link")},
         "fused_rng": {"value": world * R / (ms_fused * 1e-3), "unit": "realizations/s", "ms_per_step": ms_fused,
                       "bound": "fp32 issue / SFU (no HBM traffic beyond 32 B of counters)"},
         "e2e": e2e, "gpu_launches": launches, "clocks": sampler.summary(), "counters": final,

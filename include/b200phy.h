@@ -186,6 +186,23 @@ int b200phy_alamouti_encode(int dtype, const void *s, int64_t batch, int T, void
 int b200phy_alamouti_decode(int dtype, const void *H, const void *y, int64_t batch, int Nr, int T,
                             void *out, void *stream);
 
+/* Thin SVD of a batch of small channel matrices, always in double (what SVDMimo / GMDMimo take from
+ * np.linalg.svd, mimo.py:855-898, 974-1019): H dev complex128[batch][Nr][Nt], 1 <= Nt <= Nr <= 4 ->
+ * U dev complex128[batch][Nr][Nt], S dev double[batch][Nt] (descending), V dev complex128[batch][Nt][Nt]
+ * with H = U diag(S) V^H.  Gauge: the largest-magnitude entry of every column of V is real positive
+ * (numpy's gauge is LAPACK's; the two differ by one unit phase per singular pair). */
+int b200phy_svd(const void *H, int64_t batch, int Nr, int Nt, void *U, double *S, void *V, void *stream);
+/* util.misc.gmd (misc.py:18-159, tol = 0) for a batch: U dev complex128[batch][Nr][Nt], S dev
+ * double[batch][Nt], V dev complex128[batch][Nt][Nt] (V, not V^H) -> Q like U, R dev double[batch][Nt][Nt]
+ * (upper triangular, constant diagonal), P like V, with U diag(S) V^H = Q R P^H. */
+int b200phy_gmd(const void *U, const double *S, const void *V, int64_t batch, int Nr, int Nt, void *Q,
+                double *R, void *P, void *stream);
+/* Y = A X: A dev complex[rows][cols] (rows, cols <= 8), X dev complex[cols][n] -> Y dev complex[rows][n];
+ * the W.dot(X) / G_H.dot(Y) of SVDMimo / GMDMimo / MRT encode and decode (mimo.py:737-783, 900-948,
+ * 1021-1067). */
+int b200phy_mat_apply(int dtype, const void *A, int rows, int cols, const void *X, int64_t n, void *Y,
+                      void *stream);
+
 /* ---- fused link ops (throughput path) ------------------------------------------
  * Each covers realizations/frames [first_unit, first_unit + n_units).  Draw arrays are
  * "stream mode" inputs; pass them all NULL for "fused mode" (in-kernel Philox).
@@ -214,6 +231,20 @@ int b200phy_link_blast(int dtype, const b200phy_modem *modem, int Nr, int Nt, in
                        double filter_noise_var, uint64_t seed, uint64_t first_unit, int64_t n_units,
                        const uint8_t *idx, const void *H, const void *noise, uint8_t *idx_hat,
                        void *dec_out, int64_t *counters, void *stream);
+
+/* Channel-dependent precoding over flat Rayleigh (simulate_mimo.py:68-142 with mimo.SVDMimo,
+ * mimo.GMDMimo or mimo.MRT; mimo.py:666-783, 829-1067).  SVD / GMD: square Nr == Nt in [2, 4], Nt layers,
+ * symbol p = l*S + s of a realization is layer l at time s (X = transmit_data.reshape(Nt, -1));
+ * filter_noise_var > 0 selects the MMSE filter of the GMD equivalent channel, else ZF (ignored by SVD
+ * and MRT).  MRT: Nr == 1, one layer.  idx dev uint8[n][S*layers], H dev complex[n][Nr][Nt],
+ * noise dev complex[n][Nr][S]. */
+#define B200PHY_MIMO_SVD 1
+#define B200PHY_MIMO_GMD 2
+#define B200PHY_MIMO_MRT 3
+int b200phy_link_precoded(int dtype, const b200phy_modem *modem, int scheme, int Nr, int Nt, int S,
+                          double noise_var, double filter_noise_var, uint64_t seed, uint64_t first_unit,
+                          int64_t n_units, const uint8_t *idx, const void *H, const void *noise,
+                          uint8_t *idx_hat, void *dec_out, int64_t *counters, void *stream);
 
 /* OFDM over Jakes/TDL, SISO or Blast-MIMO (see b200phy_ofdm_tdl_params).
  * idx dev uint8[n][Nt*n_sym*used]; phi, psi dev real[n][L][n_taps][Nr][Nt];

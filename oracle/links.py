@@ -89,6 +89,32 @@ def blast_flat(modem, idx, H, n, noise_var, filter_noise_var=0.0):
     return modem.demodulate(dec), dec
 
 
+def precoded_flat(modem, scheme, idx, H, n, noise_var, filter_noise_var=0.0):
+    """SVDMimo / GMDMimo / MRT over flat Rayleigh (apps/mimo/simulate_mimo.py:68-142): idx[U, S*layers] with
+    symbol p = l*S + s on layer l (X = reshape(Nt, -1)), H[U, Nr, Nt], n[U, Nr, S].  The SVD is the
+    gauge-fixed one (mimo.svd_canonical): the convention of the CUDA decomposition."""
+    U = idx.shape[0]
+    Nr, Nt = H.shape[1:]
+    dec = np.empty(idx.shape, dtype=complex)
+    for u in range(U):
+        sym = modem.modulate(idx[u])
+        if scheme == 'mrt':
+            y = np.dot(H[u], mimo.mrt_encode(sym, H[u])) + n[u] * np.sqrt(noise_var)
+            dec[u] = mimo.mrt_decode(y, H[u])
+            continue
+        Uc, Sc, Vc = mimo.svd_canonical(H[u])
+        if scheme == 'svd':
+            W = Vc / np.sqrt(Nt)
+            G = np.diag(1.0 / Sc).dot(Uc.conj().T) * np.sqrt(Nt)
+        else:
+            Q, R, P = mimo.gmd(Uc, Sc, Vc.conj().T)
+            W = P / np.sqrt(Nt)
+            G = mimo.blast_receive_filter(Q.dot(R), filter_noise_var)
+        y = np.dot(H[u], mimo.precoded_encode(sym, W)) + n[u] * np.sqrt(noise_var)
+        dec[u] = G.dot(y).reshape(-1)
+    return modem.demodulate(dec), dec
+
+
 # ---- OFDM over a Jakes-TDL channel ---------------------------------------
 class OfdmTdlConfig:
     def __init__(self, modem, fft, cp, used=None, n_sym=1, Nr=1, Nt=1,

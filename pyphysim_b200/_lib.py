@@ -76,6 +76,12 @@ SIGNATURES = {
     'b200phy_link_blast': (C.c_int, [C.c_int, _MP, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double,
                                      C.c_uint64, C.c_uint64, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp,
                                      _vp]),
+    'b200phy_link_precoded': (C.c_int, [C.c_int, _MP, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double,
+                                        C.c_double, C.c_uint64, C.c_uint64, C.c_int64, _vp, _vp, _vp, _vp,
+                                        _vp, _vp, _vp]),
+    'b200phy_svd': (C.c_int, [_vp, C.c_int64, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
+    'b200phy_gmd': (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
+    'b200phy_mat_apply': (C.c_int, [C.c_int, _vp, C.c_int, C.c_int, _vp, C.c_int64, _vp, _vp]),
     'b200phy_link_ofdm_tdl': (C.c_int, [_PP, _MP, C.c_uint64, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp,
                                         _vp, _vp]),
     'b200phy_draw_siso_flat': (C.c_int, [C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_int64, _vp, _vp,

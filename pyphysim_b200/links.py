@@ -231,6 +231,36 @@ def link_blast(modulator, noise_var, n_units, *, Nr=2, Nt=2, num_symbols=1, filt
     return _finish(cnt, own, [hat, dec])
 
 
+MIMO_SCHEMES = {'svd': 1, 'gmd': 2, 'mrt': 3}
+
+
+def link_precoded(modulator, noise_var, n_units, *, scheme, Nr, Nt, num_symbols=1, filter_noise_var=0.0,
+                  seed=SEED_DEFAULT, first_unit=0, dtype='f32', draws=None, counters=None,
+                  want_idx=False, want_samples=False):
+    """SVDMimo / GMDMimo (square Nr == Nt, Nt layers) or MRT (Nr == 1, one layer) over flat Rayleigh:
+    one channel realization per unit, decomposed on the GPU, `num_symbols` symbol vectors through
+    precoder -> channel -> receive filter.  Symbol p = l * num_symbols + s is layer l at time s."""
+    lib = _lib.load()
+    torch = _lib.torch_cuda()
+    dt = _lib.parse_dtype(dtype)
+    if scheme not in MIMO_SCHEMES:
+        raise ValueError("scheme must be one of %s" % sorted(MIMO_SCHEMES))
+    modem, keep = _modem(modulator, dt)
+    cnt, own = _counters(torch, counters)
+    idx = H = noise = None
+    if draws is not None:
+        idx, H, noise = draws
+    S = num_symbols
+    layers = 1 if scheme == 'mrt' else Nt
+    hat = torch.empty((n_units, S * layers), dtype=torch.uint8, device='cuda') if want_idx else None
+    dec = torch.empty((n_units, S * layers), dtype=_lib.cplx_dtype(dt), device='cuda') if want_samples else None
+    _lib.check(lib.b200phy_link_precoded(dt, modem, MIMO_SCHEMES[scheme], Nr, Nt, S, float(noise_var),
+                                         float(filter_noise_var), seed, first_unit, n_units, _lib.ptr(idx),
+                                         _lib.ptr(H), _lib.ptr(noise), _lib.ptr(hat), _lib.ptr(dec),
+                                         _lib.ptr(cnt), _lib.cur_stream()))
+    return _finish(cnt, own, [hat, dec])
+
+
 def draw_flat_mimo(modulator, n_units, *, Nr, Nt, num_symbols, n_data, seed=SEED_DEFAULT, first_unit=0,
                    dtype='f32'):
     """(idx u8[n, n_data], H[n, Nr, Nt], noise[n, Nr, num_symbols]) of fused mode."""

@@ -100,6 +100,37 @@ def randn_c(*args, seed=None, dtype=np.complex128, device_out=False):
     return out if shape else complex(out)
 
 
+def gmd(U, S, V_H, tol=0.0):
+    """util/misc.py:18-159: geometric mean decomposition A = Q R P^H from an SVD A = U diag(S) V_H, on the
+    GPU (``b200phy_gmd``).  Shapes follow the reference: U [m, m] (or thin [m, n]), S [n], V_H [n, n] ->
+    Q like U, R [m, n] real upper triangular with constant diagonal, P [n, n].  All singular values must be
+    kept (every S >= tol) and n <= m <= 4."""
+    lib = _lib.load()
+    torch = _lib.torch_cuda()
+    U = np.asarray(U, dtype=np.complex128)
+    S = np.asarray(S, dtype=np.float64)
+    V = np.ascontiguousarray(np.asarray(V_H, dtype=np.complex128).conj().T)
+    m, n = U.shape[0], V.shape[0]
+    if int(np.sum(S >= tol)) < 1:
+        raise RuntimeError("This is no singular value greater than the tolerance")
+    if int(np.sum(S >= tol)) != n or S.size != n:
+        raise NotImplementedError("gmd on the GPU keeps every singular value (tol drops %d of %d)"
+                                  % (n - int(np.sum(S >= tol)), n))
+    u, _ = D.to_device(np.ascontiguousarray(U[:, :n]), np.complex128)
+    s, _ = D.to_device(S, np.float64)
+    v, _ = D.to_device(V, np.complex128)
+    q = torch.empty_like(u)
+    r = torch.empty((n, n), dtype=torch.float64, device='cuda')
+    p = torch.empty_like(v)
+    _lib.check(lib.b200phy_gmd(_lib.ptr(u), _lib.ptr(s), _lib.ptr(v), 1, m, n, _lib.ptr(q), _lib.ptr(r),
+                               _lib.ptr(p), _lib.cur_stream()))
+    Q = U.copy()
+    Q[:, :n] = q.cpu().numpy()
+    R = np.zeros((m, n))
+    R[:n, :] = r.cpu().numpy()
+    return Q, R, p.cpu().numpy()
+
+
 def qfunc(x):
     """util/misc.py:569-592 (host scalar; theory curves only)."""
     return 0.5 * math.erfc(x / math.sqrt(2))

@@ -130,6 +130,69 @@ def test_mimo(golden):
                                    g[name + '_dec'], **TOL)
 
 
+def test_mimo_schemes(golden):
+    """next-3: MRT / MRC / SVDMimo / GMDMimo, gmd() and the post-processing SINRs against the reference
+    (tests/golden/make_golden_mimo_schemes.py).  SVD-based outputs use numpy's SVD exactly as the reference
+    does, so they are compared tightly; the gauge-fixed SVD the CUDA path uses is checked against them
+    through the gauge-invariant products."""
+    g = golden('mimo_schemes')
+    nv = float(g['noise_var'])
+    for n in (2, 3, 4):
+        pre = 'sq%d_' % n
+        H, x, noise = g[pre + 'H'], g[pre + 'x'], g[pre + 'noise']
+        Q, R, P = mimo.gmd(g[pre + 'U'], g[pre + 'S'], g[pre + 'Vh'])
+        for got, ref in ((Q, g[pre + 'Q']), (R, g[pre + 'R']), (P, g[pre + 'P'])):
+            assert np.array_equal(got, ref)                       # same arithmetic on the same SVD: bit exact
+        np.testing.assert_allclose(Q.dot(R).dot(P.conj().T), H, rtol=1e-12, atol=1e-13)
+        np.testing.assert_allclose(np.diag(R), np.prod(g[pre + 'S']) ** (1.0 / n) * np.ones(n), rtol=1e-13)
+        for name, Wf, Gf in (('svd', mimo.svd_precoder, lambda h: mimo.svd_receive_filter(h)),
+                             ('gmd', mimo.gmd_precoder, lambda h: mimo.gmd_receive_filter(h, nv))):
+            W, G = Wf(H), Gf(H)
+            np.testing.assert_allclose(W, g[pre + name + '_W'], **TOL)
+            np.testing.assert_allclose(G, g[pre + name + '_G'], rtol=1e-9, atol=1e-10)
+            enc = mimo.precoded_encode(x, W)
+            np.testing.assert_allclose(enc, g[pre + name + '_enc'], **TOL)
+            np.testing.assert_allclose(G.dot(H.dot(enc) + noise).reshape(-1), g[pre + name + '_dec'], rtol=1e-9, atol=1e-10)
+            sin = mimo.post_processing_linear_sinrs(H, W, G, nv)
+            # the reference's calc_linear_SINRs returns dB (it calls calc_post_processing_SINRs, mimo.py:311-333)
+            np.testing.assert_allclose(10 * np.log10(sin), g[pre + name + '_sinr_lin'], rtol=1e-8, atol=1e-9)
+            assert int(g[pre + name + '_layers']) == n
+        # gauge-fixed SVD: same singular values, and the SVD filters differ from numpy's by one unit phase
+        # per stream that cancels in G H W
+        U, S, V = mimo.svd_canonical(H)
+        np.testing.assert_allclose(S, g[pre + 'S'], rtol=1e-13)
+        np.testing.assert_allclose(U.dot(np.diag(S)).dot(V.conj().T), H, rtol=1e-12, atol=1e-13)
+        Wc, Gc = V / math.sqrt(n), np.diag(1 / S).dot(U.conj().T) * math.sqrt(n)
+        np.testing.assert_allclose(Gc.dot(H).dot(Wc), np.eye(n), rtol=1e-10, atol=1e-11)
+        D = np.diag(Wc.conj().T.dot(g[pre + 'svd_W'])) * n
+        np.testing.assert_allclose(np.abs(D), np.ones(n), rtol=1e-12)
+        np.testing.assert_allclose(mimo.post_processing_linear_sinrs(H, Wc, Gc, nv),
+                                   mimo.post_processing_linear_sinrs(H, g[pre + 'svd_W'], g[pre + 'svd_G'], nv), rtol=1e-9)
+    Q, R, P = mimo.gmd(g['tall_U'], g['tall_S'], g['tall_Vh'])
+    assert np.array_equal(Q, g['tall_Q']) and np.array_equal(R, g['tall_R']) and np.array_equal(P, g['tall_P'])
+    Q, R, P = mimo.gmd(g['tol_U'], g['tol_S'], g['tol_Vh'], float(g['tol_tol']))
+    assert np.array_equal(Q, g['tol_Q']) and np.array_equal(R, g['tol_R']) and np.array_equal(P, g['tol_P'])
+    for nt in (2, 3, 4):
+        pre = 'mrt%d_' % nt
+        h, x, noise = g[pre + 'h'], g[pre + 'x'], g[pre + 'noise']
+        np.testing.assert_allclose(mimo.mrt_precoder(h), g[pre + 'W'], **TOL)
+        np.testing.assert_allclose(mimo.mrt_receive_filter(h), g[pre + 'G'], **TOL)
+        enc = mimo.mrt_encode(x, h)
+        np.testing.assert_allclose(enc, g[pre + 'enc'], **TOL)
+        np.testing.assert_allclose(mimo.mrt_decode(h.dot(enc) + noise, h), g[pre + 'dec'], **TOL)
+        sin = mimo.post_processing_linear_sinrs(h, mimo.mrt_precoder(h), mimo.mrt_receive_filter(h), nv)
+        np.testing.assert_allclose(10 * np.log10(sin), g[pre + 'sinr_lin'].reshape(-1), rtol=1e-9)
+    # MRC = Blast with a column channel (mimo.py:786-826)
+    h = g['mrc_h'][:, None]
+    enc = mimo.blast_encode(g['mrc_x'], 1)
+    np.testing.assert_allclose(enc, g['mrc_enc'], **TOL)
+    np.testing.assert_allclose(mimo.blast_decode(h.dot(enc) + g['mrc_noise'], h, nv), g['mrc_dec'], rtol=1e-9, atol=1e-10)
+    assert int(g['mrc_layers']) == 1
+    H = g['mrc2_H']
+    enc = mimo.blast_encode(g['mrc2_x'], 3)
+    np.testing.assert_allclose(mimo.blast_decode(H.dot(enc) + g['mrc2_noise'], H), g['mrc2_dec'], rtol=1e-9, atol=1e-10)
+
+
 def test_link_c3_full_size(golden):
     g = golden('links')
     m = links.Modem('qam', 64)
