@@ -1,3 +1,3 @@
-"""Mirror of pyphysim.channels for the single-link hot path (fading generators, TDL channel,
-single-user channel wrappers)."""
-from . import fading, fading_generators, singleuser  # noqa: F401
+"""Mirror of pyphysim.channels: fading generators, TDL channel, single-user channel wrappers and the
+multi-link grids (MuChannel / MuMimoChannel)."""
+from . import fading, fading_generators, multiuser, singleuser  # noqa: F401
