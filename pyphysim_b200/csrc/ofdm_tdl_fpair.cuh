@@ -23,7 +23,7 @@ ofdm_tdl_fpair_kernel(const __grid_constant__ OfdmP p, const Modem m, const cx<f
 
     unsigned char *sp = smem_raw;
     auto take = [&](size_t bytes) { unsigned char *r = sp; sp += (bytes + 15) & ~size_t(15); return r; };
-    cx<T> *tw = (cx<T> *)take(sizeof(cx<T>) * fft);
+    cx<T> *tw = (cx<T> *)take(sizeof(cx<T>) * (fft + kTwc));
     float4 *E2 = (float4 *)take(sizeof(float4) * (mem + S));            // [tail | cp | body], lanes = frames
     float4 *body = E2 + mem + cp;
     float4 *pool = (float4 *)take(sizeof(float4) * 2 * fft);            // rx buffer + scratch
@@ -40,6 +40,7 @@ ofdm_tdl_fpair_kernel(const __grid_constant__ OfdmP p, const Modem m, const cx<f
         sincospi(-2.0 * double(i) / double(fft), &s, &c);
         tw[i] = {T(c), T(s)};
     }
+    fill_compact_twiddles(tw, fft);
     if (m.kind != B200PHY_MODEM_BPSK)
         for (int k = tid; k < m.M; k += kOT) tab[k] = tab_g[k];
     __syncthreads();
@@ -394,7 +395,7 @@ ofdm_tdl_fpair_kernel(const __grid_constant__ OfdmP p, const Modem m, const cx<f
 inline size_t ofdm_tdl_fpair_smem(const OfdmP &p, int M) {
     auto al = [](size_t b) { return (b + 15) & ~size_t(15); };
     size_t s = 0;
-    s += al(sizeof(cx<float>) * p.fft);
+    s += al(sizeof(cx<float>) * (p.fft + kTwc));
     s += al(sizeof(float4) * (p.mem + p.S));
     s += al(sizeof(float4) * 2 * p.fft);
     s += al(sizeof(u64) * p.n_taps * 2);

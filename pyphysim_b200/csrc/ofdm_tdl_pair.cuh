@@ -41,20 +41,55 @@ __device__ __forceinline__ ps mul_w(ps v, float wre, float wim) {
     return {fma2(v.im, NWI, mul2(v.re, WR)), fma2(v.im, WR, mul2(v.re, WI))};
 }
 
+// The twiddle table tw[N] (w^i = e^{-2 pi j i / N}) is followed by kTwc compact per-stage tables for the
+// radix-4 stages with Ns = 4, 16, 64: stage Ns keeps (w^{k s}, w^{2 k s}, w^{3 k s}), s = N / (4 Ns), k < Ns,
+// as three contiguous runs at offset Ns - 4.  Reading them from the full table costs 4- to 16-way shared
+// memory bank conflicts in exactly these stages (stride s * 8 B between lanes; ncu: 13 M of the kernel's
+// 23 M excess wavefronts).
+constexpr int kTwc = 252;
+
+__device__ inline void fill_compact_twiddles(cx<float> *tw, int N) {
+    cx<float> *twc = tw + N;
+    for (int e = threadIdx.x; e < kTwc; e += blockDim.x) {
+        const int Ns = e < 12 ? 4 : (e < 60 ? 16 : 64);
+        const int r = e - (Ns - 4), m = r / Ns + 1, k = r - (m - 1) * Ns;
+        cx<float> w = {1.f, 0.f};
+        if (4 * Ns <= N) {
+            double s, c;
+            sincospi(-2.0 * double(m * k * (N / (4 * Ns))) / double(N), &s, &c);
+            w = {float(c), float(s)};
+        }
+        twc[e] = w;
+    }
+}
+
 // Stockham radix-4 (+ radix-2) FFT on pair samples; same structure as fft_stockham
 template <bool INV>
 __device__ float4 *fft_stockham_pair(float4 *a, float4 *b, const cx<float> *tw, int N, int lg) {
     float4 *src = a, *dst = b;
     int Ns = 1;
+    // The first stage writes 4 consecutive elements per lane (64 B stride between lanes: a 4-way bank conflict
+    // on every STS.128).  Its output buffer is therefore XOR-swizzled in the low 3 index bits,
+    // a -> a ^ swz(a >> 3), which spreads a quarter-warp over all 8 bank groups; the second stage reads it
+    // back through the same swizzle (a constant XOR per aligned group of 8 lanes: still conflict-free).
+    auto swz = [](int x) { return (x & 3) | (((x >> 1) & 1) << 2); };
+    const bool sw = (lg >> 1) >= 2 && N >= 64;
     for (int st = 0; st < (lg >> 1); ++st) {
         __syncthreads();
         const int q = N >> 2;
         for (int j = threadIdx.x; j < q; j += blockDim.x) {
             const int k = j & (Ns - 1);
-            ps v0 = ld_ps(src + j), v1 = ld_ps(src + j + q), v2 = ld_ps(src + j + 2 * q), v3 = ld_ps(src + j + 3 * q);
+            const int jl = (sw && st == 1) ? (j ^ swz(j >> 3)) : j;
+            ps v0 = ld_ps(src + jl), v1 = ld_ps(src + jl + q), v2 = ld_ps(src + jl + 2 * q), v3 = ld_ps(src + jl + 3 * q);
             if (Ns > 1) {
-                const int ts = k << (lg - 2 - 2 * st);
-                const cx<float> w1 = tw[ts], w2 = tw[2 * ts], w3 = tw[3 * ts];
+                cx<float> w1, w2, w3;
+                if (Ns <= 64) {
+                    const cx<float> *t = tw + N + (Ns - 4) + k;
+                    w1 = t[0]; w2 = t[Ns]; w3 = t[2 * Ns];
+                } else {
+                    const int ts = k << (lg - 2 - 2 * st);
+                    w1 = tw[ts]; w2 = tw[2 * ts]; w3 = tw[3 * ts];
+                }
                 v1 = mul_w(v1, w1.re, INV ? -w1.im : w1.im);
                 v2 = mul_w(v2, w2.re, INV ? -w2.im : w2.im);
                 v3 = mul_w(v3, w3.re, INV ? -w3.im : w3.im);
@@ -64,11 +99,21 @@ __device__ float4 *fft_stockham_pair(float4 *a, float4 *b, const cx<float> *tw, 
             ps y1, y3;
             if (INV) { y1 = {sub2(a1.re, a3.im), add2(a1.im, a3.re)}; y3 = {add2(a1.re, a3.im), sub2(a1.im, a3.re)}; }
             else     { y1 = {add2(a1.re, a3.im), sub2(a1.im, a3.re)}; y3 = {sub2(a1.re, a3.im), add2(a1.im, a3.re)}; }
-            const int j0 = ((j - k) << 2) + k;
-            st_ps(dst + j0, a0 + a2);
-            st_ps(dst + j0 + Ns, y1);
-            st_ps(dst + j0 + 2 * Ns, a0 - a2);
-            st_ps(dst + j0 + 3 * Ns, y3);
+            if (sw && st == 0) {
+                const int f = swz(j >> 1);                         // (4 j + m) >> 3 == j >> 1 for m < 4
+                float4 *d4 = dst + ((4 * j) ^ (f & 4));
+                const int c = f & 3;
+                st_ps(d4 + c, a0 + a2);                            // element m goes to slot m ^ c
+                st_ps(d4 + (1 ^ c), y1);
+                st_ps(d4 + (2 ^ c), a0 - a2);
+                st_ps(d4 + (3 ^ c), y3);
+            } else {
+                const int j0 = ((j - k) << 2) + k;
+                st_ps(dst + j0, a0 + a2);
+                st_ps(dst + j0 + Ns, y1);
+                st_ps(dst + j0 + 2 * Ns, a0 - a2);
+                st_ps(dst + j0 + 3 * Ns, y3);
+            }
         }
         Ns <<= 2;
         float4 *t = src; src = dst; dst = t;
@@ -137,7 +182,7 @@ ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m, const cx<fl
 
     unsigned char *sp = smem_raw;
     auto take = [&](size_t bytes) { unsigned char *r = sp; sp += (bytes + 15) & ~size_t(15); return r; };
-    cx<T> *tw = (cx<T> *)take(sizeof(cx<T>) * fft);
+    cx<T> *tw = (cx<T> *)take(sizeof(cx<T>) * (fft + kTwc));
     float4 *E2 = (float4 *)take(sizeof(float4) * (mem + S));            // one tx pair: [tail | cp | body]
     float4 *body = E2 + mem + cp;
     float4 *pool = (float4 *)take(sizeof(float4) * (NP + 1) * fft);     // rx pair buffers + 1 scratch
@@ -154,6 +199,7 @@ ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m, const cx<fl
         sincospi(-2.0 * double(i) / double(fft), &s, &c);
         tw[i] = {T(c), T(s)};
     }
+    fill_compact_twiddles(tw, fft);
     if (m.kind != B200PHY_MODEM_BPSK)
         for (int k = tid; k < m.M; k += kOT) tab[k] = tab_g[k];
     __syncthreads();
@@ -582,7 +628,7 @@ inline size_t ofdm_tdl_pair_smem(const OfdmP &p, int M, int NR, int NT) {
     auto al = [](size_t b) { return (b + 15) & ~size_t(15); };
     const int NP = NR / 2, TP = NT / 2;
     size_t s = 0;
-    s += al(sizeof(cx<float>) * p.fft);
+    s += al(sizeof(cx<float>) * (p.fft + kTwc));
     s += al(sizeof(float4) * (p.mem + p.S));
     s += al(sizeof(float4) * (NP + 1) * p.fft);
     s += al(sizeof(cx<float>) * p.n_taps * NR * NT);
