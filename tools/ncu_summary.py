@@ -1,0 +1,30 @@
+#!/usr/bin/env python
+"""Dump the judged metrics of every kernel in an .ncu-rep as `metric,unit,value` CSV (what profiles/*_ncu_metrics.csv hold).
+usage: tools/ncu_summary.py report.ncu-rep > profiles/<name>_ncu_metrics.csv"""
+import csv
+import subprocess
+import sys
+
+WANT = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
+        'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'sm__throughput.avg.pct_of_peak_sustained_elapsed',
+        'smsp__inst_executed.sum', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
+        'sm__warps_active.avg.pct_of_peak_sustained_active', 'launch__registers_per_thread',
+        'launch__shared_mem_per_block_dynamic', 'launch__grid_size', 'launch__block_size',
+        'launch__occupancy_limit_registers', 'launch__occupancy_limit_shared_mem',
+        'sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active',
+        'sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active',
+        'sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active',
+        'sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active',
+        'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum', 'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum',
+        'sass__inst_executed_local_loads', 'sass__inst_executed_local_stores',
+        'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_tensor.sum']
+out = subprocess.run(['ncu', '-i', sys.argv[1], '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+rows = list(csv.reader(out.splitlines()))
+hdr, units = rows[0], rows[1]
+for vals in rows[2:]:
+    print('kernel,,%s' % vals[hdr.index('Kernel Name')].split('(')[0])
+    print('metric,unit,value')
+    for w in WANT:
+        if w in hdr:
+            i = hdr.index(w)
+            print('%s,%s,%s' % (w, units[i], vals[i].replace(',', '')))
