@@ -203,6 +203,41 @@ int b200phy_gmd(const void *U, const double *S, const void *V, int64_t batch, in
 int b200phy_mat_apply(int dtype, const void *A, int rows, int cols, const void *X, int64_t n, void *Y,
                       void *stream);
 
+/* ---- reference signals and pilot-based channel estimation ------------- */
+
+/* One user's reference-signal sequence, generated on the device in double and stored in `dtype`:
+ *   out[n] = scale * base[n mod Nzc] * exp(j 2 pi n_cs n / denominator),  n < size
+ * base = exp(-j pi u m (m + 1 + 2q) / Nzc) (calcBaseZC, reference_signals/zadoffchu.py:11-36), or, when
+ * phi_table (host int8[Nzc], Nzc = 12 or 24: a row of 3GPP TS 36.211 Table 5.5.1.2-1 / -2) is given,
+ * base = exp(j pi phi[m] / 4) (RootSequence, root_sequence.py:273-283).  n mod Nzc is the cyclic extension
+ * (get_extended_ZF, zadoffchu.py:75-113); the shift is get_shifted_root_seq (:39-72) with denominator 8
+ * for SRS (srs.py:23-48) and 12 for DMRS (dmrs.py:19-41); `scale` carries the cover-code entry and the
+ * normalisation of UeSequence (srs.py:71-93).  out dev complex[size]. */
+int b200phy_refsig_sequence(int dtype, int Nzc, int u, double q_re, double q_im, const int8_t *phi_table,
+                            int size, int n_cs, int denominator, double scale_re, double scale_im, void *out,
+                            void *stream);
+
+/* CazacBasedChannelEstimator.estimate_channel_freq_domain (reference_signals/channel_estimation.py:69-131)
+ * for a batch of received vectors, with the cover-code average of CazacBasedWithOCCChannelEstimator
+ * (:163-251) folded in: z = conj(ref) * mean_c(cover[c] * y[c]); taps = ifft(z, Nsc)[0 : num_taps_to_keep+1];
+ * out = scale * fft(taps, size_multiplier * Nsc).  ref dev complex[Nsc]; y dev complex[batch][n_cover][Nsc];
+ * cover host double[2*n_cover] (re, im) or NULL (= ones), n_cover <= 4; out dev complex[batch][size_multiplier*Nsc]. */
+int b200phy_cazac_estimate(int dtype, const void *ref_seq, const void *y, const double *cover_re_im, int n_cover,
+                           int64_t batch, int Nsc, int num_taps_to_keep, int size_multiplier, double scale,
+                           void *out, void *stream);
+
+/* compute_ls_estimation (channel_estimation/estimators.py:12-61): H = Y s^H (s s^H)^-1 per realization.
+ * Y dev complex[batch][Nr][P]; s dev complex[batch][Nt][P] (s_per_unit = 1) or complex[Nt][P] shared by all
+ * realizations (s_per_unit = 0); out dev complex[batch][Nr][Nt].  Nt <= 4. */
+int b200phy_ls_estimate(int dtype, const void *Y, const void *s, int s_per_unit, int64_t batch, int Nr, int Nt,
+                        int P, void *out, void *stream);
+
+/* compute_mmse_estimation (estimators.py:100-174), one transmit antenna:
+ * h = (noise_power I + P C)^-1 C (Y s^H) P / (s s^H).  Y, s as above with Nt = 1; C host complex128[Nr][Nr]
+ * as (re, im) doubles; out dev complex[batch][Nr].  Nr <= 8. */
+int b200phy_mmse_estimate(int dtype, const void *Y, const void *s, int s_per_unit, int64_t batch, int Nr, int P,
+                          double noise_power, const double *C_re_im, void *out, void *stream);
+
 /* ---- fused link ops (throughput path) ------------------------------------------
  * Each covers realizations/frames [first_unit, first_unit + n_units).  Draw arrays are
  * "stream mode" inputs; pass them all NULL for "fused mode" (in-kernel Philox).

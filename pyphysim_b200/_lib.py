@@ -82,6 +82,13 @@ SIGNATURES = {
     'b200phy_svd': (C.c_int, [_vp, C.c_int64, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
     'b200phy_gmd': (C.c_int, [_vp, _vp, _vp, C.c_int64, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
     'b200phy_mat_apply': (C.c_int, [C.c_int, _vp, C.c_int, C.c_int, _vp, C.c_int64, _vp, _vp]),
+    'b200phy_refsig_sequence': (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, _vp, C.c_int, C.c_int,
+                                          C.c_int, C.c_double, C.c_double, _vp, _vp]),
+    'b200phy_cazac_estimate': (C.c_int, [C.c_int, _vp, _vp, _f64p, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int,
+                                         C.c_double, _vp, _vp]),
+    'b200phy_ls_estimate': (C.c_int, [C.c_int, _vp, _vp, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int, _vp, _vp]),
+    'b200phy_mmse_estimate': (C.c_int, [C.c_int, _vp, _vp, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_double, _f64p,
+                                        _vp, _vp]),
     'b200phy_link_ofdm_tdl': (C.c_int, [_PP, _MP, C.c_uint64, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp,
                                         _vp, _vp]),
     'b200phy_draw_siso_flat': (C.c_int, [C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_int64, _vp, _vp,
