@@ -55,6 +55,15 @@ static int fill_params(const b200phy_ofdm_tdl_params *q, const Modem &m, OfdmP *
         p.delays[l] = q->delays[l];
         p.amp[l] = sqrt(q->tap_powers[l] / double(q->L));
     }
+    {
+        int j = 0;
+        for (int c = 0; c < 4; ++c) {
+            p.cls_start[c] = j;
+            for (int l = 0; l < q->n_taps; ++l)
+                if ((q->delays[l] & 3) == c) { p.cls_pos[l] = j; p.cls_delay[j] = q->delays[l]; ++j; }
+        }
+        p.cls_start[4] = j;
+    }
     p.w0 = 2.0 * M_PI * q->Fd;
     p.Ts1 = q->Ts * 1.0000000001;
     p.t0 = q->t0;

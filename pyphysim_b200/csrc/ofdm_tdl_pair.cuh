@@ -186,7 +186,7 @@ ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m, const cx<fl
     float4 *E2 = (float4 *)take(sizeof(float4) * (mem + S));            // one tx pair: [tail | cp | body]
     float4 *body = E2 + mem + cp;
     float4 *pool = (float4 *)take(sizeof(float4) * (NP + 1) * fft);     // rx pair buffers + 1 scratch
-    cx<T> *gbar = (cx<T> *)take(sizeof(cx<T>) * p.n_taps * NR * NT);
+    float4 *gb2 = (float4 *)take(sizeof(float4) * p.n_taps * NT * NP);  // mean taps [class-sorted tap][t][rx pair]
     float4 *tails = (float4 *)take(p.n_sym > 1 ? sizeof(float4) * TP * mem : 0);
     u64 *coef = (u64 *)take(sizeof(u64) * p.n_taps * NP * 2 * 4 * 2);   // [tap][rx pair][t in pair][order][re|im]
     cx<T> *tab = (cx<T> *)take(sizeof(cx<T>) * m.M);
@@ -409,8 +409,9 @@ ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m, const cx<fl
                         cq[0] = a0.re; cq[2] = a0.im; cq[4] = a1.re; cq[6] = a1.im;
                         cq[8] = a2.re; cq[10] = a2.im; cq[12] = a3.re; cq[14] = a3.im;
                         const T m1 = T(p.mu[0][l]), m2 = T(p.mu[1][l]), m3 = T(p.mu[2][l]);
-                        gbar[(l * NR + r) * NT + t] = {a0.re + m1 * a1.re + m2 * a2.re + m3 * a3.re,
-                                                       a0.im + m1 * a1.im + m2 * a2.im + m3 * a3.im};
+                        T *gq = reinterpret_cast<T *>(gb2 + (p.cls_pos[l] * NT + t) * NP + (r >> 1)) + (r & 1);
+                        gq[0] = a0.re + m1 * a1.re + m2 * a2.re + m3 * a3.re;
+                        gq[2] = a0.im + m1 * a1.im + m2 * a2.im + m3 * a3.im;
                     }
                 }
                 // ---------------- B: paired IFFT (ends in E2.body), cyclic prefix, ISI tail
@@ -536,81 +537,135 @@ ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m, const cx<fl
                 if (res != Yp[q]) { W = Yp[q]; Yp[q] = res; }
             }
 
-            // ---------------- G: H_k, detect, demap, count (as in ofdm_tdl.cuh)
+            // ---------------- G: H_k, detect, demap, count.  H_k = sum_l gbar_l W^{k d_l} on rx-pair lanes (FFMA2):
+            // a thread owns the NU bins k0 + u fft/NU; with NU = 4, W^{(k0 + u fft/4) d} = W^{k0 d} (-j)^{u d}, so the
+            // taps are summed per residue class d mod 4 (host-sorted, OfdmP::cls_*) and the four class sums are
+            // combined by a 4-point DFT.
             constexpr int NU = (NR * NT <= 4) ? 4 : 1;
             const int kstride = fft / NU;
+            uint8_t *hat_fs = idx_hat ? idx_hat + size_t(frame) * p.n_data + size_t(s) * p.used * NT : nullptr;
+            cx<T> *eq_fs = eq_out ? eq_out + size_t(frame) * p.n_data + size_t(s) * p.used * NT : nullptr;
+            const bool hat_vec = (reinterpret_cast<uintptr_t>(hat_fs) & (NT - 1)) == 0;
             for (int k0 = tid; k0 < kstride; k0 += kOT) {
-                cx<T> H[NU][NR][NT];
+                ps Hc[NU][NT][NP];
 #pragma unroll
                 for (int u = 0; u < NU; ++u)
 #pragma unroll
-                    for (int r = 0; r < NR; ++r)
+                    for (int t = 0; t < NT; ++t)
 #pragma unroll
-                        for (int t = 0; t < NT; ++t) H[u][r][t] = {0.f, 0.f};
-                for (int l = 0; l < p.n_taps; ++l) {
-                    const int d = p.delays[l];
-                    const cx<T> w = tw[(k0 * d) & (fft - 1)];
-                    const cx<T> *gl = gbar + l * NR * NT;
-                    if constexpr (NU == 4) {
-                        switch (d & 3) {
-                            case 0: hk_class<T, NR, NT, 0>(H, gl, w); break;
-                            case 1: hk_class<T, NR, NT, 1>(H, gl, w); break;
-                            case 2: hk_class<T, NR, NT, 2>(H, gl, w); break;
-                            default: hk_class<T, NR, NT, 3>(H, gl, w); break;
-                        }
-                    } else {
+                        for (int q = 0; q < NP; ++q) Hc[u][t][q] = {0ull, 0ull};
+                auto tap_sum = [&](ps (&acc)[NT][NP], int j0, int j1) {
+                    for (int j = j0; j < j1; ++j) {
+                        const cx<T> w = tw[(k0 * p.cls_delay[j]) & (fft - 1)];
+                        const u64 WR = pk2(w.re, w.re), WI = pk2(w.im, w.im), NWI = pk2(-w.im, -w.im);
 #pragma unroll
-                        for (int r = 0; r < NR; ++r)
+                        for (int t = 0; t < NT; ++t)
 #pragma unroll
-                            for (int t = 0; t < NT; ++t) cmac(H[0][r][t], gl[r * NT + t], w);
+                            for (int q = 0; q < NP; ++q) {
+                                const ps g = ld_ps(gb2 + (j * NT + t) * NP + q);
+                                acc[t][q].re = fma2(g.im, NWI, fma2(g.re, WR, acc[t][q].re));
+                                acc[t][q].im = fma2(g.im, WR, fma2(g.re, WI, acc[t][q].im));
+                            }
                     }
-                }
+                };
                 if constexpr (NU == 4) {
 #pragma unroll
-                    for (int r = 0; r < NR; ++r)
+                    for (int c = 0; c < 4; ++c) tap_sum(Hc[c], p.cls_start[c], p.cls_start[c + 1]);
 #pragma unroll
-                        for (int t = 0; t < NT; ++t) {
-                            const cx<T> a0 = H[0][r][t] + H[2][r][t], a1 = H[0][r][t] - H[2][r][t];
-                            const cx<T> a2 = H[1][r][t] + H[3][r][t], a3 = H[1][r][t] - H[3][r][t];
-                            const cx<T> rot = {a3.im, -a3.re};
-                            H[0][r][t] = a0 + a2;
-                            H[1][r][t] = a1 + rot;
-                            H[2][r][t] = a0 - a2;
-                            H[3][r][t] = a1 - rot;
+                    for (int t = 0; t < NT; ++t)
+#pragma unroll
+                        for (int q = 0; q < NP; ++q) {
+                            const ps a0 = Hc[0][t][q] + Hc[2][t][q], a1 = Hc[0][t][q] - Hc[2][t][q];
+                            const ps a2 = Hc[1][t][q] + Hc[3][t][q], a3 = Hc[1][t][q] - Hc[3][t][q];
+                            Hc[0][t][q] = a0 + a2;
+                            Hc[1][t][q] = {add2(a1.re, a3.im), sub2(a1.im, a3.re)};      // a1 - j a3
+                            Hc[2][t][q] = a0 - a2;
+                            Hc[3][t][q] = {sub2(a1.re, a3.im), add2(a1.im, a3.re)};      // a1 + j a3
                         }
+                } else {
+                    tap_sum(Hc[0], 0, p.n_taps);
                 }
+                // detection of the NU bins: branch-free arithmetic first (independent double chains of the bins
+                // overlap), then demap / count / store under the bin's validity predicate
+                cx<T> z[NU][NT];
+                int qv[NU];
 #pragma unroll
                 for (int u = 0; u < NU; ++u) {
                     const int k = k0 + u * kstride;
-                    const int q = pos_of(k, fft, p.used, p.half);
-                    if (q < 0) continue;
-                    cx<T> y[NR];
+                    qv[u] = pos_of(k, fft, p.used, p.half);
+                    cx<T> H[NR][NT], y[NR];
 #pragma unroll
                     for (int qq = 0; qq < NP; ++qq) {
+#pragma unroll
+                        for (int t = 0; t < NT; ++t) {
+                            upk2(Hc[u][t][qq].re, H[2 * qq][t].re, H[2 * qq + 1][t].re);
+                            upk2(Hc[u][t][qq].im, H[2 * qq][t].im, H[2 * qq + 1][t].im);
+                        }
                         const float4 v = Yp[qq][k];
                         y[2 * qq] = {rx_scale * v.x, rx_scale * v.z};
                         y[2 * qq + 1] = {rx_scale * v.y, rx_scale * v.w};
                     }
-                    HermSolver<NT> sol;
-                    sol.template factor_from_channel<cx<T>, NR>(H[u], NR, p.fnv);
-                    cx<double> b[NT];
+                    if constexpr (NT == 2) {
+                        // closed-form 2x2 (H^H H + s2 I)^-1 H^H y in double; 1/det by one Newton step on the float
+                        // reciprocal (relative error 4e-15) instead of a double division
+                        double a = p.fnv, bb = p.fnv;
+                        cx<double> c = {0.0, 0.0}, v0 = {0.0, 0.0}, v1 = {0.0, 0.0};
 #pragma unroll
-                    for (int t = 0; t < NT; ++t) {
-                        b[t] = {0.0, 0.0};
+                        for (int r = 0; r < NR; ++r) {
+                            const cx<double> h0 = cvt<double>(H[r][0]), h1 = cvt<double>(H[r][1]), yr = cvt<double>(y[r]);
+                            a += norm2(h0);
+                            bb += norm2(h1);
+                            cmac_conj(c, h1, h0);
+                            cmac_conj(v0, h0, yr);
+                            cmac_conj(v1, h1, yr);
+                        }
+                        const double det = a * bb - norm2(c);
+                        double rd = double(__frcp_rn(float(det)));
+                        rd = rd * fma(-det, rd, 2.0);
+                        const double g = rd * p.snt;
+                        z[u][0] = {T(g * (bb * v0.re - (c.re * v1.re + c.im * v1.im))), T(g * (bb * v0.im - (c.re * v1.im - c.im * v1.re)))};
+                        z[u][1] = {T(g * (a * v1.re - (c.re * v0.re - c.im * v0.im))), T(g * (a * v1.im - (c.re * v0.im + c.im * v0.re)))};
+                    } else {
+                        HermSolver<NT> sol;
+                        sol.template factor_from_channel<cx<T>, NR>(H, NR, p.fnv);
+                        cx<double> b[NT];
 #pragma unroll
-                        for (int r = 0; r < NR; ++r) cmac_conj(b[t], cvt<double>(H[u][r][t]), cvt<double>(y[r]));
+                        for (int t = 0; t < NT; ++t) {
+                            b[t] = {0.0, 0.0};
+#pragma unroll
+                            for (int r = 0; r < NR; ++r) cmac_conj(b[t], cvt<double>(H[r][t]), cvt<double>(y[r]));
+                        }
+                        sol.solve(b);
+#pragma unroll
+                        for (int t = 0; t < NT; ++t) z[u][t] = {T(b[t].re * p.snt), T(b[t].im * p.snt)};
                     }
-                    sol.solve(b);
+                }
 #pragma unroll
-                    for (int t = 0; t < NT; ++t) {
-                        const cx<T> z = {T(b[t].re * p.snt), T(b[t].im * p.snt)};
-                        const int a = dsym[q * NT + t];
-                        const int e = demap_symbol<T>(m, tab, z);
-                        sym_err += (e != a);
-                        bit_err += __popc(e ^ a);
-                        const size_t o = size_t(frame) * p.n_data + size_t(s * p.used + q) * NT + t;
-                        if (idx_hat) idx_hat[o] = uint8_t(e);
-                        if (eq_out) eq_out[o] = z;
+                for (int u = 0; u < NU; ++u) {
+                    const int q = qv[u];
+                    if (q < 0) continue;
+                    // the NT symbols of this subcarrier are adjacent (Blast layer interleave): one packed compare / store
+                    unsigned av, ev = 0;
+                    if constexpr (NT == 2) av = *reinterpret_cast<const uint16_t *>(dsym + q * NT);
+                    else av = *reinterpret_cast<const uint32_t *>(dsym + q * NT);
+#pragma unroll
+                    for (int t = 0; t < NT; ++t) ev |= unsigned(demap_symbol<T>(m, tab, z[u][t])) << (8 * t);
+                    const unsigned x = ev ^ av;
+                    bit_err += __popc(x);
+#pragma unroll
+                    for (int t = 0; t < NT; ++t) sym_err += ((x >> (8 * t)) & 0xffu) != 0u;
+                    if (hat_fs) {
+                        if (hat_vec) {
+                            if constexpr (NT == 2) *reinterpret_cast<uint16_t *>(hat_fs + q * NT) = uint16_t(ev);
+                            else *reinterpret_cast<uint32_t *>(hat_fs + q * NT) = ev;
+                        } else {
+#pragma unroll
+                            for (int t = 0; t < NT; ++t) hat_fs[q * NT + t] = uint8_t(ev >> (8 * t));
+                        }
+                    }
+                    if (eq_fs) {
+#pragma unroll
+                        for (int t = 0; t < NT; ++t) eq_fs[q * NT + t] = z[u][t];
                     }
                 }
             }
@@ -631,7 +686,7 @@ inline size_t ofdm_tdl_pair_smem(const OfdmP &p, int M, int NR, int NT) {
     s += al(sizeof(cx<float>) * (p.fft + kTwc));
     s += al(sizeof(float4) * (p.mem + p.S));
     s += al(sizeof(float4) * (NP + 1) * p.fft);
-    s += al(sizeof(cx<float>) * p.n_taps * NR * NT);
+    s += al(sizeof(float4) * p.n_taps * NT * NP);
     s += al(p.n_sym > 1 ? sizeof(float4) * TP * p.mem : 0);
     s += al(sizeof(u64) * p.n_taps * NP * 2 * 4 * 2);
     s += al(sizeof(cx<float>) * M);
