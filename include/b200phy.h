@@ -45,7 +45,11 @@ enum {
                                 (Modulator.demodulate, modulators/fundamental.py:241-248) */
     B200PHY_MODEM_QAM = 1,   /* square Gray QAM built by QAM.__init__ (fundamental.py:659-777):
                                 per-axis slicer, identical decisions to the table search */
-    B200PHY_MODEM_BPSK = 2   /* BPSK.modulate/demodulate (fundamental.py:605-647) */
+    B200PHY_MODEM_BPSK = 2,  /* BPSK.modulate/demodulate (fundamental.py:605-647) */
+    B200PHY_MODEM_QPSK = 3   /* QPSK() = PSK(4, pi/4) with its Gray order (fundamental.py:396-448, 510-531):
+                                symbols[i] lies in the quadrant (re < 0 iff bit 0, im < 0 iff bit 1), so the
+                                min-distance search is a quadrant slicer with identical decisions (ties on the
+                                axes, a null set, go to the lower index like argmin); map still reads the table */
 };
 
 enum {

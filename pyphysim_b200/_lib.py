@@ -13,7 +13,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('B200PHY_LIB') or os.path.join(PKG, 'libb200phy.so')   # override: A/B builds
 
 F32, F64 = 0, 1
-MODEM_TABLE, MODEM_QAM, MODEM_BPSK = 0, 1, 2
+MODEM_TABLE, MODEM_QAM, MODEM_BPSK, MODEM_QPSK = 0, 1, 2, 3
 JAKES_AUTO, JAKES_RECURRENCE, JAKES_POLY = 0, 1, 2
 ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_RANGE = 1, 2, 3, 4
 MAX_TAPS, MAX_RAYS, MAX_ANT = 32, 64, 4

@@ -109,6 +109,7 @@ __device__ __forceinline__ int demap_symbol(const Modem &m, const cx<T> *__restr
         g ^= (g >> 1) & m.m1;
         return int(g);
     }
+    if (m.kind == B200PHY_MODEM_QPSK) return int(r.re < T(0)) | (int(r.im < T(0)) << 1);
     if (m.kind == B200PHY_MODEM_BPSK) {
         // NumPy orders complex numbers lexicographically: (r < 0) == re<0 or (re==0 and im<0)
         return (r.re < T(0) || (r.re == T(0) && r.im < T(0))) ? 1 : 0;

@@ -37,6 +37,8 @@ int check_modem(const b200phy_modem *m, Modem *out) {
         if (b & 1) { set_error("M must be a square power of 2"); return B200PHY_ERR_INVALID; }
     } else if (m->kind == B200PHY_MODEM_BPSK) {
         if (M != 2) { set_error("BPSK requires M=2"); return B200PHY_ERR_INVALID; }
+    } else if (m->kind == B200PHY_MODEM_QPSK) {
+        if (M != 4) { set_error("QPSK requires M=4"); return B200PHY_ERR_INVALID; }
     } else if (m->kind != B200PHY_MODEM_TABLE) {
         set_error("unknown modem kind %d", m->kind);
         return B200PHY_ERR_INVALID;

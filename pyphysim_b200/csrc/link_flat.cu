@@ -152,14 +152,16 @@ siso_flat_kernel(Modem m_in, const cx<T> *__restrict__ tab_g, T sigma, uint64_t 
 
 // ================================================================= Alamouti flat
 // One realization per thread: H[Nr][2], S symbols (S/2 codewords), noise[Nr][S].
-template <typename T, bool FUSED, int NR, bool DEC>
-__global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 4 : 2)
-alamouti_kernel(Modem m, const cx<T> *__restrict__ tab_g, int S, T sigma, uint64_t seed,
+template <typename T, bool FUSED, int NR, bool DEC, bool QPSK>
+__global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 5 : 2)
+alamouti_kernel(Modem m_in, const cx<T> *__restrict__ tab_g, int S, T sigma, uint64_t seed,
                 uint64_t first_unit, long long n, const uint8_t *__restrict__ idx,
                 const cx<T> *__restrict__ Hg, const cx<T> *__restrict__ noise,
                 uint8_t *__restrict__ idx_hat, cx<T> *__restrict__ dec_out,
                 unsigned long long *counters) {
     __shared__ cx<T> tab[256];
+    Modem m = m_in;
+    if (QPSK) m.kind = B200PHY_MODEM_QPSK;    // compile-time kind: the quadrant slicer is inlined without branches
     stage_table(m, tab_g, tab);
     unsigned sym_err = 0, bit_err = 0;
     const T rs2 = T(0.70710678118654752440);
@@ -397,12 +399,15 @@ static int launch_alamouti(const Modem &m, const void *table, int Nr, int S, dou
                                         (long long)n, idx, (const cx<T> *)H, (const cx<T> *)noise,
                                         idx_hat, (cx<T> *)dec, (unsigned long long *)counters);
     };
-#define B200_ALA2(F, N_) do { if (dec) args(alamouti_kernel<T, F, N_, true>); else args(alamouti_kernel<T, F, N_, false>); } while (0)
+    const bool qpsk = m.kind == B200PHY_MODEM_QPSK;
+#define B200_ALA3(F, N_, D_) do { if (qpsk) args(alamouti_kernel<T, F, N_, D_, true>); else args(alamouti_kernel<T, F, N_, D_, false>); } while (0)
+#define B200_ALA2(F, N_) do { if (dec) B200_ALA3(F, N_, true); else B200_ALA3(F, N_, false); } while (0)
 #define B200_ALA(F) do { switch (Nr) { case 1: B200_ALA2(F, 1); break; case 2: B200_ALA2(F, 2); break; \
                                         case 3: B200_ALA2(F, 3); break; default: B200_ALA2(F, 4); } } while (0)
     if (fused) B200_ALA(true); else B200_ALA(false);
 #undef B200_ALA
 #undef B200_ALA2
+#undef B200_ALA3
     B200_CHECK_LAUNCH("alamouti_kernel");
     return B200PHY_OK;
 }

@@ -9,14 +9,16 @@
 
 namespace b200phy {
 
-template <bool FUSED>
+template <bool FUSED, bool QAMK>
 __global__ void __launch_bounds__(kOT, 3)
-ofdm_tdl_fpair_kernel(const __grid_constant__ OfdmP p, const Modem m, const cx<float> *__restrict__ tab_g,
+ofdm_tdl_fpair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const cx<float> *__restrict__ tab_g,
                       uint64_t first_unit, long long n_pairs, const uint8_t *__restrict__ idx_g,
                       const float *__restrict__ phi_g, const float *__restrict__ psi_g,
                       const cx<float> *__restrict__ noise_g, uint8_t *__restrict__ idx_hat,
                       cx<float> *__restrict__ eq_out, unsigned long long *counters) {
     using T = float;
+    Modem m = m_in;
+    if (QAMK) m.kind = B200PHY_MODEM_QAM;      // compile-time kind (see ofdm_tdl_pair_kernel)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x;
     const int fft = p.fft, S = p.S, mem = p.mem, cp = p.cp;

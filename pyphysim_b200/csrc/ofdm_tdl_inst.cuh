@@ -39,11 +39,11 @@ static int launch_one(const OfdmP &p, const Modem &m, const void *table, uint64_
     return e;
 }
 
-template <bool FUSED, int NR, int NT>
-static int launch_pair(const OfdmP &p, const Modem &m, const void *table, uint64_t first_unit, int64_t n_units,
+template <bool FUSED, int NR, int NT, bool QAMK>
+static int launch_pair_k(const OfdmP &p, const Modem &m, const void *table, uint64_t first_unit, int64_t n_units,
                        const uint8_t *idx, const void *phi, const void *psi, const void *noise,
                        uint8_t *idx_hat, void *eq_out, int64_t *counters, size_t smem, cudaStream_t st) {
-    auto kern = ofdm_tdl_pair_kernel<FUSED, NR, NT>;
+    auto kern = ofdm_tdl_pair_kernel<FUSED, NR, NT, QAMK>;
     int e = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)),
                        "cudaFuncSetAttribute(ofdm_tdl_pair_kernel)");
     if (e) return e;
@@ -63,11 +63,20 @@ static int launch_pair(const OfdmP &p, const Modem &m, const void *table, uint64
     return check_cuda(cudaGetLastError(), "ofdm_tdl_pair_kernel launch");
 }
 
-template <bool FUSED>
-static int launch_fpair(const OfdmP &p, const Modem &m, const void *table, uint64_t first_unit, int64_t n_pairs,
+template <bool FUSED, int NR, int NT>
+static int launch_pair(const OfdmP &p, const Modem &m, const void *table, uint64_t first_unit, int64_t n_units,
+                       const uint8_t *idx, const void *phi, const void *psi, const void *noise,
+                       uint8_t *idx_hat, void *eq_out, int64_t *counters, size_t smem, cudaStream_t st) {
+    if (m.kind == B200PHY_MODEM_QAM)
+        return launch_pair_k<FUSED, NR, NT, true>(p, m, table, first_unit, n_units, idx, phi, psi, noise, idx_hat, eq_out, counters, smem, st);
+    return launch_pair_k<FUSED, NR, NT, false>(p, m, table, first_unit, n_units, idx, phi, psi, noise, idx_hat, eq_out, counters, smem, st);
+}
+
+template <bool FUSED, bool QAMK>
+static int launch_fpair_k(const OfdmP &p, const Modem &m, const void *table, uint64_t first_unit, int64_t n_pairs,
                         const uint8_t *idx, const void *phi, const void *psi, const void *noise,
                         uint8_t *idx_hat, void *eq_out, int64_t *counters, size_t smem, cudaStream_t st) {
-    auto kern = ofdm_tdl_fpair_kernel<FUSED>;
+    auto kern = ofdm_tdl_fpair_kernel<FUSED, QAMK>;
     int e = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)),
                        "cudaFuncSetAttribute(ofdm_tdl_fpair_kernel)");
     if (e) return e;
@@ -85,6 +94,15 @@ static int launch_fpair(const OfdmP &p, const Modem &m, const void *table, uint6
                                        idx_hat, (cx<float> *)eq_out, (unsigned long long *)counters);
     count_launch();
     return check_cuda(cudaGetLastError(), "ofdm_tdl_fpair_kernel launch");
+}
+
+template <bool FUSED>
+static int launch_fpair(const OfdmP &p, const Modem &m, const void *table, uint64_t first_unit, int64_t n_pairs,
+                        const uint8_t *idx, const void *phi, const void *psi, const void *noise,
+                        uint8_t *idx_hat, void *eq_out, int64_t *counters, size_t smem, cudaStream_t st) {
+    if (m.kind == B200PHY_MODEM_QAM)
+        return launch_fpair_k<FUSED, true>(p, m, table, first_unit, n_pairs, idx, phi, psi, noise, idx_hat, eq_out, counters, smem, st);
+    return launch_fpair_k<FUSED, false>(p, m, table, first_unit, n_pairs, idx, phi, psi, noise, idx_hat, eq_out, counters, smem, st);
 }
 
 template <typename T, int NR, int NT>

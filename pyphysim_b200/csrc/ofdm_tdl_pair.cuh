@@ -167,15 +167,19 @@ __device__ __forceinline__ void ray_moments_f32(cx<float> (&a)[4], const float *
     }
 }
 
-template <bool FUSED, int NR, int NT>
+// QAMK: the modem kind is square Gray QAM at compile time (the slicer is inlined, the table-search / PSK paths
+// are not even in the binary: ~10 % less code in a kernel whose hot path does not fit the instruction cache)
+template <bool FUSED, int NR, int NT, bool QAMK>
 __global__ void __launch_bounds__(kOT, (NR * NT <= 4) ? 3 : 1)
-ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m, const cx<float> *__restrict__ tab_g,
+ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const cx<float> *__restrict__ tab_g,
                      uint64_t first_unit, long long n_units, const uint8_t *__restrict__ idx_g,
                      const float *__restrict__ phi_g, const float *__restrict__ psi_g,
                      const cx<float> *__restrict__ noise_g, uint8_t *__restrict__ idx_hat,
                      cx<float> *__restrict__ eq_out, unsigned long long *counters) {
     using T = float;
     constexpr int NP = NR / 2, TP = NT / 2;
+    Modem m = m_in;
+    if (QAMK) m.kind = B200PHY_MODEM_QAM;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x;
     const int fft = p.fft, S = p.S, mem = p.mem, cp = p.cp;
@@ -555,6 +559,9 @@ ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m, const cx<fl
 #pragma unroll
                         for (int q = 0; q < NP; ++q) Hc[u][t][q] = {0ull, 0ull};
                 auto tap_sum = [&](ps (&acc)[NT][NP], int j0, int j1) {
+#ifdef B200_HK_NOUNROLL
+#pragma unroll 1
+#endif
                     for (int j = j0; j < j1; ++j) {
                         const cx<T> w = tw[(k0 * p.cls_delay[j]) & (fft - 1)];
                         const u64 WR = pk2(w.re, w.re), WI = pk2(w.im, w.im), NWI = pk2(-w.im, -w.im);

@@ -161,6 +161,11 @@ class QPSK(PSK):
 
     def __init__(self):
         super().__init__(4, PI / 4.)
+        self._kind = _lib.MODEM_QPSK          # Gray QPSK: the device demaps with a quadrant slicer
+
+    def setConstellation(self, symbols):
+        self._kind = _lib.MODEM_TABLE         # any other table (setPhaseOffset drops the Gray order): full search
+        super().setConstellation(symbols)
 
     def __repr__(self):
         return "QPSK object"

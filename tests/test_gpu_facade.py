@@ -85,6 +85,24 @@ def test_demodulate_matches_reference(golden):
     assert np.mean(hat32 != g['qam64_hat']) < 1e-3
 
 
+def test_qpsk_slicer_and_table_fallback():
+    """QPSK() demaps with the quadrant slicer (B200PHY_MODEM_QPSK): same indices as the oracle's min-distance
+    search on 1e6 noisy points; after setPhaseOffset (the reference rebuilds WITHOUT the Gray order,
+    fundamental.py:450-459) the object falls back to the table search and still matches."""
+    from oracle import modulators as omd
+    from pyphysim_b200 import _lib
+    from pyphysim_b200.modulators import QPSK
+    q = QPSK()
+    assert q._kind == _lib.MODEM_QPSK
+    r = 1.2 * philox.cnormal(SEED, 2, [77], 1000000)[0]
+    ref = omd.demodulate(q.symbols, r)
+    assert np.array_equal(q.demodulate(r), ref)
+    assert np.array_equal(q.demodulate(q.modulate(np.arange(4))), np.arange(4))
+    q.setPhaseOffset(0.3)
+    assert q._kind == _lib.MODEM_TABLE
+    assert np.array_equal(q.demodulate(r[:100000]), omd.demodulate(q.symbols, r[:100000]))
+
+
 def test_theoretical_curves():
     from pyphysim_b200.modulators import BPSK, PSK, QAM
     # numbers asserted by the reference's tests (tests/modulators_package_test.py:72-138, 282-322)

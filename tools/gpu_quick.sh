@@ -1,6 +1,6 @@
 # quick GPU iteration: the OFDM/TDL parity tests, then short device-timed bench lines (no CPU leg)
 mkdir -p gpurun_out/q
-timeout 600 python -m pytest tests/test_gpu_ofdm_tdl.py -m gpu -x -q 2>&1 | tail -5
+timeout 600 python -m pytest tests/test_gpu_ofdm_tdl.py -m gpu -x -q 2>&1 | tail -${TAILN:-5}
 for w in ofdm1024_qam64_mimo2x2_tdl c3_ofdm1024_qam64_siso_tdl c5_ofdm2048_qam256_mimo4x4_tdl; do
   timeout 300 python bench.py --workload $w --no-cpu --steps 5 > gpurun_out/q/$w.json 2>gpurun_out/q/$w.err
   python - "$w" <<'PY'
