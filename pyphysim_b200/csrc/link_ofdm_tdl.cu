@@ -57,10 +57,11 @@ static int fill_params(const b200phy_ofdm_tdl_params *q, const Modem &m, OfdmP *
     }
     {
         int j = 0;
-        for (int c = 0; c < 4; ++c) {
-            p.cls_start[c] = j;
+        const int order[4] = {0, 2, 1, 3};           // runs of d mod 4; the classes mod 2 stay contiguous
+        for (int i = 0; i < 4; ++i) {
+            p.cls_start[i] = j;
             for (int l = 0; l < q->n_taps; ++l)
-                if ((q->delays[l] & 3) == c) { p.cls_pos[l] = j; p.cls_delay[j] = q->delays[l]; ++j; }
+                if ((q->delays[l] & 3) == order[i]) { p.cls_pos[l] = j; p.cls_delay[j] = q->delays[l]; ++j; }
         }
         p.cls_start[4] = j;
     }

@@ -45,8 +45,8 @@ struct OfdmP {
     int ifft_in_w;  // 1: scatter into W so that the ping-pong IFFT ends in E.body
     int delays[B200PHY_MAX_TAPS];
     // taps grouped by delay residue class d mod 4 (the H_k evaluation of the pair kernels sums each class
-    // separately and combines the four sums with a 4-point DFT): class c occupies sorted positions
-    // [cls_start[c], cls_start[c+1]); cls_pos[l] = sorted position of tap l, cls_delay[j] = its delay
+    // separately and combines the sums with a 4- or 2-point DFT): run i = class (0, 2, 1, 3)[i] occupies sorted
+    // positions [cls_start[i], cls_start[i+1]); cls_pos[l] = sorted position of tap l, cls_delay[j] = its delay
     int cls_start[5], cls_pos[B200PHY_MAX_TAPS], cls_delay[B200PHY_MAX_TAPS];
     double amp[B200PHY_MAX_TAPS];   // sqrt(P_l / L)
     double mu[3][B200PHY_MAX_TAPS]; // mean of tau^p (p = 1..3) over the S samples of a symbol, per tap

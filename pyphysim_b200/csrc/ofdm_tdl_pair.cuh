@@ -222,12 +222,13 @@ ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const cx
     // into shared memory while this frame is in the FIR (one OFDM symbol per frame only: then the phase
     // buffers are free after the ray setup).  `apipe`: the raw noise rows of an rx pair are copied into that
     // pair's (still unused) accumulator buffer at frame start and merged in the FIR epilogue.
-    // The data symbols of the next frame (<= 8 B per thread) wait in two registers instead.
-    const bool pf = !FUSED && p.n_sym == 1 && (p.n_data & 7) == 0 && p.n_data <= 8 * kOT &&
+    // The data symbols of the next frame (8 B per thread and 2048 symbols) wait in registers instead.
+    constexpr int kPre = (NR * NT <= 4) ? 1 : NT;
+    const bool pf = !FUSED && p.n_sym == 1 && (p.n_data & 7) == 0 && p.n_data <= 8 * kOT * kPre &&
                     (reinterpret_cast<uintptr_t>(idx_g) & 7) == 0;
     const bool pf16 = pf && (p.P & 3) == 0 && aligned16(phi_g) && aligned16(psi_g);
-    const bool apipe = !FUSED && fft == kOT * kJBC;
-    uint2 idx_pre = make_uint2(0u, 0u);
+    const bool apipe = !FUSED;
+    uint2 idx_pre[kPre];
     auto prefetch = [&](long long f) {
         const T *gp = phi_g + size_t(f) * p.P, *gq = psi_g + size_t(f) * p.P;
         if (pf16) {
@@ -241,7 +242,10 @@ ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const cx
                 cp_async<4>(ph_psi + i, gq + i);
             }
         }
-        if (tid < (p.n_data >> 3)) idx_pre = __ldg(reinterpret_cast<const uint2 *>(idx_g + size_t(f) * p.n_data) + tid);
+#pragma unroll
+        for (int u = 0; u < kPre; ++u)
+            if (tid + u * kOT < (p.n_data >> 3))
+                idx_pre[u] = __ldg(reinterpret_cast<const uint2 *>(idx_g + size_t(f) * p.n_data) + tid + u * kOT);
     };
     if constexpr (!FUSED) {
         if (pf && blockIdx.x < n_units) prefetch(blockIdx.x);
@@ -268,7 +272,9 @@ ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const cx
             }
         } else if (pf) {
             cp_async_wait<0>();                      // prefetched during the previous frame (visible after the barrier below)
-            if (tid < (p.n_data >> 3)) reinterpret_cast<uint2 *>(dsym)[tid] = idx_pre;
+#pragma unroll
+            for (int u = 0; u < kPre; ++u)
+                if (tid + u * kOT < (p.n_data >> 3)) reinterpret_cast<uint2 *>(dsym)[tid + u * kOT] = idx_pre[u];
         } else {
             const T *gp = phi_g + size_t(frame) * p.P, *gq = psi_g + size_t(frame) * p.P;
             for (int i0 = tid; i0 < p.P; i0 += 4 * kOT) {
@@ -319,16 +325,17 @@ ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const cx
                         if (j + 1 >= 0 && j + 1 < fft) { const cx<T> c = sigma * cnormal<T>(blk.z, blk.w); yr[4 * j + 4] = c.re; yr[4 * j + 6] = c.im; }
                     }
                 } else if (apipe) {
-                    // raw rows (rx 2q | rx 2q+1) into the pair buffer; merged into pair layout after the FIR
+                    // raw noise of rx 2q / 2q+1 at sample j lands in the two halves of the float4 slot j of the pair
+                    // buffer (n0.re, n0.im, n1.re, n1.im); the FIR epilogue turns each slot into pair layout in
+                    // place.  A thread consumes only slots it copied itself, so its own wait_group is enough.
                     const size_t rowlen = size_t(p.N + mem);
 #pragma unroll
                     for (int q = 0; q < NP; ++q) {
                         const cx<T> *s0 = noise_g + (size_t(frame) * NR + 2 * q) * rowlen + m0, *s1 = s0 + rowlen;
                         cx<T> *raw = reinterpret_cast<cx<T> *>(Yp[q]);
-#pragma unroll
-                        for (int jb = 0; jb < kJBC; ++jb) {
-                            cp_async<8>(raw + tid + jb * kOT, s0 + tid + jb * kOT);
-                            cp_async<8>(raw + fft + tid + jb * kOT, s1 + tid + jb * kOT);
+                        for (int j = tid; j < fft; j += kOT) {
+                            cp_async<8>(raw + 2 * j, s0 + j);
+                            cp_async<8>(raw + 2 * j + 1, s1 + j);
                         }
                     }
                     cp_async_commit();
@@ -488,29 +495,20 @@ ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const cx
                         };
                         if (p.porder == 3) taps(std::true_type{}); else taps(std::false_type{});
                         if (!FUSED && apipe && tp == 0) {
-                            // the raw noise rows have landed in Yp[q]: y = sigma * noise + FIR, re-laid as pairs
+                            // the raw noise has landed in this thread's slots: y = sigma * noise + FIR, re-laid as pairs
                             if (TP == 1) cp_async_wait<1>(); else cp_async_wait<0>();
-                            __syncthreads();
-                            cx<T> n0[kJBC][NP], n1[kJBC][NP];
-#pragma unroll
-                            for (int jb = 0; jb < kJBC; ++jb)
-#pragma unroll
-                                for (int q = 0; q < NP; ++q) {
-                                    const cx<T> *raw = reinterpret_cast<const cx<T> *>(Yp[q]);
-                                    n0[jb][q] = raw[tid + jb * kOT];
-                                    n1[jb][q] = raw[fft + tid + jb * kOT];
-                                }
-                            __syncthreads();
                             const u64 sg = pk2(sigma, sigma);
 #pragma unroll
                             for (int jb = 0; jb < kJBC; ++jb)
 #pragma unroll
                                 for (int q = 0; q < NP; ++q) {
+                                    float4 *slot = Yp[q] + tid + jo0 + jb * kOT;
+                                    const float4 v = *slot;          // (n0.re, n0.im, n1.re, n1.im)
                                     ps y;
                                     // rounded product then sum: bit-identical to the fused-RNG path
-                                    y.re = add2(mul2(pk2(n0[jb][q].re, n1[jb][q].re), sg), aRe[jb][q]);
-                                    y.im = add2(mul2(pk2(n0[jb][q].im, n1[jb][q].im), sg), aIm[jb][q]);
-                                    st_ps(Yp[q] + tid + jb * kOT, y);
+                                    y.re = add2(mul2(pk2(v.x, v.z), sg), aRe[jb][q]);
+                                    y.im = add2(mul2(pk2(v.y, v.w), sg), aIm[jb][q]);
+                                    st_ps(slot, y);
                                 }
                         } else {
 #pragma unroll
@@ -542,10 +540,11 @@ ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const cx
             }
 
             // ---------------- G: H_k, detect, demap, count.  H_k = sum_l gbar_l W^{k d_l} on rx-pair lanes (FFMA2):
-            // a thread owns the NU bins k0 + u fft/NU; with NU = 4, W^{(k0 + u fft/4) d} = W^{k0 d} (-j)^{u d}, so the
-            // taps are summed per residue class d mod 4 (host-sorted, OfdmP::cls_*) and the four class sums are
-            // combined by a 4-point DFT.
-            constexpr int NU = (NR * NT <= 4) ? 4 : 1;
+            // a thread owns the NU bins k0 + u fft/NU; W^{(k0 + u fft/NU) d} = W^{k0 d} e^{-2 pi j u d / NU}, so the
+            // taps are summed per residue class d mod NU (host-sorted runs in the class order 0, 2, 1, 3:
+            // OfdmP::cls_*, so that the classes mod 2 are contiguous too) and the class sums are combined by an
+            // NU-point DFT.  NU = 4 when the 4 x NT x NP packed accumulators fit the register budget, else 2.
+            constexpr int NU = (NR * NT <= 4) ? 4 : 2;
             const int kstride = fft / NU;
             uint8_t *hat_fs = idx_hat ? idx_hat + size_t(frame) * p.n_data + size_t(s) * p.used * NT : nullptr;
             cx<T> *eq_fs = eq_out ? eq_out + size_t(frame) * p.n_data + size_t(s) * p.used * NT : nullptr;
@@ -576,8 +575,10 @@ ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const cx
                     }
                 };
                 if constexpr (NU == 4) {
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) tap_sum(Hc[c], p.cls_start[c], p.cls_start[c + 1]);
+                    tap_sum(Hc[0], p.cls_start[0], p.cls_start[1]);
+                    tap_sum(Hc[2], p.cls_start[1], p.cls_start[2]);
+                    tap_sum(Hc[1], p.cls_start[2], p.cls_start[3]);
+                    tap_sum(Hc[3], p.cls_start[3], p.cls_start[4]);
 #pragma unroll
                     for (int t = 0; t < NT; ++t)
 #pragma unroll
@@ -590,7 +591,16 @@ ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const cx
                             Hc[3][t][q] = {sub2(a1.re, a3.im), add2(a1.im, a3.re)};      // a1 + j a3
                         }
                 } else {
-                    tap_sum(Hc[0], 0, p.n_taps);
+                    tap_sum(Hc[0], p.cls_start[0], p.cls_start[2]);          // even delays
+                    tap_sum(Hc[1], p.cls_start[2], p.cls_start[4]);          // odd delays
+#pragma unroll
+                    for (int t = 0; t < NT; ++t)
+#pragma unroll
+                        for (int q = 0; q < NP; ++q) {
+                            const ps e = Hc[0][t][q], o = Hc[1][t][q];
+                            Hc[0][t][q] = e + o;
+                            Hc[1][t][q] = e - o;
+                        }
                 }
                 // detection of the NU bins: branch-free arithmetic first (independent double chains of the bins
                 // overlap), then demap / count / store under the bin's validity predicate
