@@ -63,7 +63,7 @@ ofdm_tdl_fpair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const c
     const bool pf = !FUSED && p.n_sym == 1 && (p.n_data & 3) == 0 && 2 * p.n_data <= 8 * kOT &&
                     (reinterpret_cast<uintptr_t>(idx_g) & 7) == 0;
     const bool pf16 = pf && (p.P & 3) == 0 && aligned16(phi_g) && aligned16(psi_g);
-    const bool apipe = !FUSED && fft == kOT * kJBC;
+    const bool apipe = !FUSED;
     uint2 idx_pre = make_uint2(0u, 0u);
     auto prefetch = [&](long long f) {               // f = first frame of the pair
 #pragma unroll
@@ -155,11 +155,12 @@ ofdm_tdl_fpair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const c
                 } else if (apipe) {
                     const size_t rowlen = size_t(p.N + mem);
                     const cx<T> *s0 = noise_g + size_t(frame) * rowlen + m0, *s1 = s0 + rowlen;
+                    // sample j of frame A / frame B lands in the two halves of float4 slot j (see ofdm_tdl_pair.cuh):
+                    // in-place pair relayout in the FIR epilogue, each thread consumes only its own copies
                     cx<T> *raw = reinterpret_cast<cx<T> *>(Y);
-#pragma unroll
-                    for (int jb = 0; jb < kJBC; ++jb) {
-                        cp_async<8>(raw + tid + jb * kOT, s0 + tid + jb * kOT);
-                        cp_async<8>(raw + fft + tid + jb * kOT, s1 + tid + jb * kOT);
+                    for (int j = tid; j < fft; j += kOT) {
+                        cp_async<8>(raw + 2 * j, s0 + j);
+                        cp_async<8>(raw + 2 * j + 1, s1 + j);
                     }
                     cp_async_commit();
                 } else {
@@ -294,21 +295,17 @@ ofdm_tdl_fpair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const c
                     };
                     if (o3) taps(std::true_type{}); else taps(std::false_type{});
                     if (!FUSED && apipe) {
-                        // raw noise rows (frame A | frame B) have landed in Y: y = sigma * noise + FIR
+                        // this thread's raw noise slots have landed: y = sigma * noise + FIR, re-laid as pairs
                         cp_async_wait<1>();
-                        __syncthreads();
-                        cx<T> n0[kJBC], n1[kJBC];
-                        const cx<T> *raw = reinterpret_cast<const cx<T> *>(Y);
-#pragma unroll
-                        for (int jb = 0; jb < kJBC; ++jb) { n0[jb] = raw[tid + jb * kOT]; n1[jb] = raw[fft + tid + jb * kOT]; }
-                        __syncthreads();
                         const u64 sg = pk2(sigma, sigma);
 #pragma unroll
                         for (int jb = 0; jb < kJBC; ++jb) {
+                            float4 *slot = Y + tid + jo0 + jb * kOT;
+                            const float4 v = *slot;   // (nA.re, nA.im, nB.re, nB.im)
                             ps y;                     // rounded product then sum: bit-identical to the fused-RNG path
-                            y.re = add2(mul2(pk2(n0[jb].re, n1[jb].re), sg), sub2(aRR[jb], aII[jb]));
-                            y.im = add2(mul2(pk2(n0[jb].im, n1[jb].im), sg), add2(aRI[jb], aIR[jb]));
-                            st_ps(Y + tid + jb * kOT, y);
+                            y.re = add2(mul2(pk2(v.x, v.z), sg), sub2(aRR[jb], aII[jb]));
+                            y.im = add2(mul2(pk2(v.y, v.w), sg), add2(aRI[jb], aIR[jb]));
+                            st_ps(slot, y);
                         }
                     } else {
 #pragma unroll

@@ -63,62 +63,108 @@ __device__ inline void fill_compact_twiddles(cx<float> *tw, int N) {
     }
 }
 
-// Stockham radix-4 (+ radix-2) FFT on pair samples; same structure as fft_stockham
+// ---- Stockham radix-4 (+ radix-2) FFT on pair samples; same structure as fft_stockham, split into pieces so
+// that the kernels can keep the first stage's inputs / the last stage's outputs in registers (the thread that
+// maps the symbols of bins j + i N/4 owns butterfly j of stage 0; the thread that detects bins k0 + u N/NU owns
+// butterfly k0 of the last stage), which saves a shared-memory round trip and a barrier each.
+
+// radix-4 butterfly; forward: y1 = a1 - j a3, y3 = a1 + j a3; inverse: signs swapped
 template <bool INV>
-__device__ float4 *fft_stockham_pair(float4 *a, float4 *b, const cx<float> *tw, int N, int lg) {
+__device__ __forceinline__ void bfly4(ps v0, ps v1, ps v2, ps v3, ps &y0, ps &y1, ps &y2, ps &y3) {
+    const ps a0 = v0 + v2, a1 = v0 - v2, a2 = v1 + v3, a3 = v1 - v3;
+    y0 = a0 + a2;
+    y2 = a0 - a2;
+    if (INV) { y1 = {sub2(a1.re, a3.im), add2(a1.im, a3.re)}; y3 = {add2(a1.re, a3.im), sub2(a1.im, a3.re)}; }
+    else     { y1 = {add2(a1.re, a3.im), sub2(a1.im, a3.re)}; y3 = {sub2(a1.re, a3.im), add2(a1.im, a3.re)}; }
+}
+
+__device__ __forceinline__ int fft_swz(int x) { return (x & 3) | (((x >> 1) & 1) << 2); }
+// the first stage's output buffer is XOR-swizzled when there are at least two radix-4 stages (see below)
+__device__ __forceinline__ bool fft_sw(int N, int lg) { return (lg >> 1) >= 2 && N >= 64; }
+
+// Stage 0 writes 4 consecutive elements per lane (64 B stride between lanes: a 4-way bank conflict on every
+// STS.128).  Its output buffer is therefore XOR-swizzled in the low 3 index bits, a -> a ^ swz(a >> 3), which
+// spreads a quarter-warp over all 8 bank groups; stage 1 reads it back through the same swizzle (a constant
+// XOR per aligned group of 8 lanes: still conflict-free).
+__device__ __forceinline__ void fft_store_stage0(float4 *dst, int j, bool sw, ps y0, ps y1, ps y2, ps y3) {
+    if (sw) {
+        const int f = fft_swz(j >> 1);                     // (4 j + m) >> 3 == j >> 1 for m < 4
+        float4 *d4 = dst + ((4 * j) ^ (f & 4));
+        const int c = f & 3;
+        st_ps(d4 + c, y0);                                 // element m goes to slot m ^ c
+        st_ps(d4 + (1 ^ c), y1);
+        st_ps(d4 + (2 ^ c), y2);
+        st_ps(d4 + (3 ^ c), y3);
+    } else {
+        st_ps(dst + 4 * j, y0);
+        st_ps(dst + 4 * j + 1, y1);
+        st_ps(dst + 4 * j + 2, y2);
+        st_ps(dst + 4 * j + 3, y3);
+    }
+}
+
+// twiddled inputs of butterfly j of radix-4 stage st >= 1 (Ns = 4^st)
+template <bool INV>
+__device__ __forceinline__ void fft_load_stage(const float4 *src, const cx<float> *tw, int N, int lg, int st, int Ns,
+                                               int j, bool sw, ps &v0, ps &v1, ps &v2, ps &v3) {
+    const int q = N >> 2, k = j & (Ns - 1);
+    const int jl = (sw && st == 1) ? (j ^ fft_swz(j >> 3)) : j;
+    v0 = ld_ps(src + jl); v1 = ld_ps(src + jl + q); v2 = ld_ps(src + jl + 2 * q); v3 = ld_ps(src + jl + 3 * q);
+    cx<float> w1, w2, w3;
+    if (Ns <= 64) {
+        const cx<float> *t = tw + N + (Ns - 4) + k;
+        w1 = t[0]; w2 = t[Ns]; w3 = t[2 * Ns];
+    } else {
+        const int ts = k << (lg - 2 - 2 * st);
+        w1 = tw[ts]; w2 = tw[2 * ts]; w3 = tw[3 * ts];
+    }
+    v1 = mul_w(v1, w1.re, INV ? -w1.im : w1.im);
+    v2 = mul_w(v2, w2.re, INV ? -w2.im : w2.im);
+    v3 = mul_w(v3, w3.re, INV ? -w3.im : w3.im);
+}
+
+// Runs the radix-4 stages [first_stage, lg/2) and the radix-2 tail, except the LAST pass when skip_last
+// (the caller then applies it from registers: fft_last_pass).  Data starts in `a` (natural order for stage 0,
+// stage-0 output layout for first_stage == 1) and ping-pongs with `b`; returns the buffer holding the result,
+// synchronised.  cp > 0 (never with skip_last): the last pass also writes the cyclic prefix, i.e. output
+// element o >= N - cp goes to index o - N of the result buffer as well.
+template <bool INV>
+__device__ float4 *fft_stockham_pair(float4 *a, float4 *b, const cx<float> *tw, int N, int lg, int first_stage = 0,
+                                     bool skip_last = false, int cp = 0) {
     float4 *src = a, *dst = b;
-    int Ns = 1;
-    // The first stage writes 4 consecutive elements per lane (64 B stride between lanes: a 4-way bank conflict
-    // on every STS.128).  Its output buffer is therefore XOR-swizzled in the low 3 index bits,
-    // a -> a ^ swz(a >> 3), which spreads a quarter-warp over all 8 bank groups; the second stage reads it
-    // back through the same swizzle (a constant XOR per aligned group of 8 lanes: still conflict-free).
-    auto swz = [](int x) { return (x & 3) | (((x >> 1) & 1) << 2); };
-    const bool sw = (lg >> 1) >= 2 && N >= 64;
-    for (int st = 0; st < (lg >> 1); ++st) {
+    const bool sw = fft_sw(N, lg);
+    const int nst = lg >> 1, q = N >> 2;
+    const int last4 = (lg & 1) ? nst : (skip_last ? nst - 1 : nst);       // radix-4 stages to run: [first, last4)
+    int Ns = 1 << (2 * first_stage);
+    for (int st = first_stage; st < last4; ++st) {
         __syncthreads();
-        const int q = N >> 2;
+        const bool wcp = cp > 0 && !(lg & 1) && st == nst - 1;
         for (int j = threadIdx.x; j < q; j += blockDim.x) {
-            const int k = j & (Ns - 1);
-            const int jl = (sw && st == 1) ? (j ^ swz(j >> 3)) : j;
-            ps v0 = ld_ps(src + jl), v1 = ld_ps(src + jl + q), v2 = ld_ps(src + jl + 2 * q), v3 = ld_ps(src + jl + 3 * q);
-            if (Ns > 1) {
-                cx<float> w1, w2, w3;
-                if (Ns <= 64) {
-                    const cx<float> *t = tw + N + (Ns - 4) + k;
-                    w1 = t[0]; w2 = t[Ns]; w3 = t[2 * Ns];
-                } else {
-                    const int ts = k << (lg - 2 - 2 * st);
-                    w1 = tw[ts]; w2 = tw[2 * ts]; w3 = tw[3 * ts];
-                }
-                v1 = mul_w(v1, w1.re, INV ? -w1.im : w1.im);
-                v2 = mul_w(v2, w2.re, INV ? -w2.im : w2.im);
-                v3 = mul_w(v3, w3.re, INV ? -w3.im : w3.im);
-            }
-            const ps a0 = v0 + v2, a1 = v0 - v2, a2 = v1 + v3, a3 = v1 - v3;
-            // forward: a1 -/+ j*a3 -> (re + a3.im, im - a3.re); inverse: signs swapped
-            ps y1, y3;
-            if (INV) { y1 = {sub2(a1.re, a3.im), add2(a1.im, a3.re)}; y3 = {add2(a1.re, a3.im), sub2(a1.im, a3.re)}; }
-            else     { y1 = {add2(a1.re, a3.im), sub2(a1.im, a3.re)}; y3 = {sub2(a1.re, a3.im), add2(a1.im, a3.re)}; }
-            if (sw && st == 0) {
-                const int f = swz(j >> 1);                         // (4 j + m) >> 3 == j >> 1 for m < 4
-                float4 *d4 = dst + ((4 * j) ^ (f & 4));
-                const int c = f & 3;
-                st_ps(d4 + c, a0 + a2);                            // element m goes to slot m ^ c
-                st_ps(d4 + (1 ^ c), y1);
-                st_ps(d4 + (2 ^ c), a0 - a2);
-                st_ps(d4 + (3 ^ c), y3);
+            ps y0, y1, y2, y3;
+            if (st == 0) {
+                bfly4<INV>(ld_ps(src + j), ld_ps(src + j + q), ld_ps(src + j + 2 * q), ld_ps(src + j + 3 * q), y0, y1, y2, y3);
+                fft_store_stage0(dst, j, sw, y0, y1, y2, y3);
             } else {
-                const int j0 = ((j - k) << 2) + k;
-                st_ps(dst + j0, a0 + a2);
+                ps v0, v1, v2, v3;
+                fft_load_stage<INV>(src, tw, N, lg, st, Ns, j, sw, v0, v1, v2, v3);
+                bfly4<INV>(v0, v1, v2, v3, y0, y1, y2, y3);
+                const int k = j & (Ns - 1), j0 = ((j - k) << 2) + k;
+                st_ps(dst + j0, y0);
                 st_ps(dst + j0 + Ns, y1);
-                st_ps(dst + j0 + 2 * Ns, a0 - a2);
+                st_ps(dst + j0 + 2 * Ns, y2);
                 st_ps(dst + j0 + 3 * Ns, y3);
+                if (wcp) {
+                    if (j0 >= N - cp) st_ps(dst + j0 - N, y0);
+                    if (j0 + Ns >= N - cp) st_ps(dst + j0 + Ns - N, y1);
+                    if (j0 + 2 * Ns >= N - cp) st_ps(dst + j0 + 2 * Ns - N, y2);
+                    if (j0 + 3 * Ns >= N - cp) st_ps(dst + j0 + 3 * Ns - N, y3);
+                }
             }
         }
         Ns <<= 2;
         float4 *t = src; src = dst; dst = t;
     }
-    if (lg & 1) {
+    if ((lg & 1) && !skip_last) {
         __syncthreads();
         const int h = N >> 1;
         for (int j = threadIdx.x; j < h; j += blockDim.x) {
@@ -126,13 +172,39 @@ __device__ float4 *fft_stockham_pair(float4 *a, float4 *b, const cx<float> *tw, 
             const cx<float> w = tw[k];
             const ps v0 = ld_ps(src + j), v1 = mul_w(ld_ps(src + j + h), w.re, INV ? -w.im : w.im);
             const int j0 = ((j - k) << 1) + k;
-            st_ps(dst + j0, v0 + v1);
-            st_ps(dst + j0 + Ns, v0 - v1);
+            const ps y0 = v0 + v1, y1 = v0 - v1;
+            st_ps(dst + j0, y0);
+            st_ps(dst + j0 + Ns, y1);
+            if (cp > 0) {
+                if (j0 >= N - cp) st_ps(dst + j0 - N, y0);
+                if (j0 + Ns >= N - cp) st_ps(dst + j0 + Ns - N, y1);
+            }
         }
         float4 *t = src; src = dst; dst = t;
     }
     __syncthreads();
     return src;
+}
+
+// The last pass of a forward transform whose earlier passes left their result in `src` (skip_last): outputs
+// of butterfly j, i.e. the bins j + u N/NU.  NU = 4: radix-4 pass (lg even), NU = 2: radix-2 pass (lg odd).
+template <int NU>
+__device__ __forceinline__ void fft_last_pass(const float4 *src, const cx<float> *tw, int N, int lg, int j, ps (&y)[NU]) {
+    if constexpr (NU == 4) {
+        const int st = (lg >> 1) - 1;
+        ps v0, v1, v2, v3;
+        fft_load_stage<false>(src, tw, N, lg, st, N >> 2, j, fft_sw(N, lg), v0, v1, v2, v3);
+        bfly4<false>(v0, v1, v2, v3, y[0], y[1], y[2], y[3]);
+    } else {
+        const cx<float> w = tw[j];
+        const ps v0 = ld_ps(src + j), v1 = mul_w(ld_ps(src + j + (N >> 1)), w.re, w.im);
+        y[0] = v0 + v1;
+        y[1] = v0 - v1;
+    }
+}
+// whether the last pass of an N = 2^lg transform produces exactly the NU bins of a detection thread
+__device__ __forceinline__ bool fft_last_fusable(int lg, int NU) {
+    return lg >= 4 && ((NU == 4 && !(lg & 1)) || (NU == 2 && (lg & 1)));
 }
 
 // Unscaled Taylor moments of one (tap, rx, tx) item's rays about the expansion centre,
