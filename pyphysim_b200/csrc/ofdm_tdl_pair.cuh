@@ -300,6 +300,9 @@ ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const cx
                     (reinterpret_cast<uintptr_t>(idx_g) & 7) == 0;
     const bool pf16 = pf && (p.P & 3) == 0 && aligned16(phi_g) && aligned16(psi_g);
     const bool apipe = !FUSED;
+    // rx FFT stage 0 straight from the FIR accumulators (one rx pair, one tx pair, one output block per frame)
+    constexpr bool kFuseRx0 = (NP == 1 && TP == 1 && kJBC == 4);
+    const bool rx0_fused = kFuseRx0 && fft == kOT * kJBC;
     uint2 idx_pre[kPre];
     auto prefetch = [&](long long f) {
         const T *gp = phi_g + size_t(f) * p.P, *gq = psi_g + size_t(f) * p.P;
@@ -432,19 +435,29 @@ ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const cx
             __syncthreads();
 
             for (int tp = 0; tp < TP; ++tp) {
-                // ---------------- A: map + scatter for both antennas of the tx pair
+                // ---------------- A: map + scatter for both antennas of the tx pair, fused with IFFT stage 0: the
+                // thread that maps bins j + i fft/4 owns butterfly j of the first (twiddle-free) radix-4 stage, so
+                // the mapped symbols never touch shared memory.  Also the ISI tail of the previous symbol.
                 float4 *in = in_w ? W : body;
                 float4 *other = in_w ? body : W;
-                for (int k = tid; k < fft; k += kOT) {
-                    const int q = pos_of(k, fft, p.used, p.half);
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (q >= 0) {
-                        const cx<T> s0 = map_symbol<T>(m, tab, dsym[q * NT + 2 * tp]);
-                        const cx<T> s1 = map_symbol<T>(m, tab, dsym[q * NT + 2 * tp + 1]);
-                        v = make_float4(tx_scale * s0.re, tx_scale * s1.re, tx_scale * s0.im, tx_scale * s1.im);
+                for (int j = tid; j < (fft >> 2); j += kOT) {
+                    ps v[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int q = pos_of(j + i * (fft >> 2), fft, p.used, p.half);
+                        v[i] = {0ull, 0ull};
+                        if (q >= 0) {
+                            const cx<T> s0 = map_symbol<T>(m, tab, dsym[q * NT + 2 * tp]);
+                            const cx<T> s1 = map_symbol<T>(m, tab, dsym[q * NT + 2 * tp + 1]);
+                            v[i] = {pk2(tx_scale * s0.re, tx_scale * s1.re), pk2(tx_scale * s0.im, tx_scale * s1.im)};
+                        }
                     }
-                    in[k] = v;
+                    ps y0, y1, y2, y3;
+                    bfly4<true>(v[0], v[1], v[2], v[3], y0, y1, y2, y3);
+                    fft_store_stage0(other, j, true, y0, y1, y2, y3);
                 }
+                for (int i = tid; i < mem; i += kOT)
+                    E2[i] = (s > 0) ? tails[tp * mem + i] : make_float4(0.f, 0.f, 0.f, 0.f);
                 // ---------------- C: ray setup, items (tap, rx, t in pair), G lanes per item
                 for (int it0 = 0; it0 < n_items; it0 += kOT / G) {
                     const int it = it0 + tid / G;
@@ -497,18 +510,14 @@ ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const cx
                         gq[2] = a0.im + m1 * a1.im + m2 * a2.im + m3 * a3.im;
                     }
                 }
-                // ---------------- B: paired IFFT (ends in E2.body), cyclic prefix, ISI tail
-                fft_stockham_pair<true>(in, other, tw, fft, p.lg);
+                // ---------------- B: remaining IFFT passes (end in E2.body); the last one also writes the cyclic prefix
+                fft_stockham_pair<true>(other, in, tw, fft, p.lg, 1, false, cp);
                 if constexpr (!FUSED) {
                     if (tp == TP - 1) {              // last ray setup done: the phase buffers are free
                         if (pf && frame + gridDim.x < n_units) prefetch(frame + gridDim.x);
                         cp_async_commit();
                     }
                 }
-                for (int i = tid; i < cp; i += kOT) E2[mem + i] = body[fft - cp + i];
-                for (int i = tid; i < mem; i += kOT)
-                    E2[i] = (s > 0) ? tails[tp * mem + i] : make_float4(0.f, 0.f, 0.f, 0.f);
-                __syncthreads();
 
                 // ---------------- D: FIR for both tx antennas of the pair into the rx pair buffers
                 {
@@ -566,6 +575,7 @@ ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const cx
                             }
                         };
                         if (p.porder == 3) taps(std::true_type{}); else taps(std::false_type{});
+                        ps yv[kJBC][NP];
                         if (!FUSED && apipe && tp == 0) {
                             // the raw noise has landed in this thread's slots: y = sigma * noise + FIR, re-laid as pairs
                             if (TP == 1) cp_async_wait<1>(); else cp_async_wait<0>();
@@ -574,26 +584,34 @@ ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const cx
                             for (int jb = 0; jb < kJBC; ++jb)
 #pragma unroll
                                 for (int q = 0; q < NP; ++q) {
-                                    float4 *slot = Yp[q] + tid + jo0 + jb * kOT;
-                                    const float4 v = *slot;          // (n0.re, n0.im, n1.re, n1.im)
-                                    ps y;
+                                    const float4 v = Yp[q][tid + jo0 + jb * kOT];       // (n0.re, n0.im, n1.re, n1.im)
                                     // rounded product then sum: bit-identical to the fused-RNG path
-                                    y.re = add2(mul2(pk2(v.x, v.z), sg), aRe[jb][q]);
-                                    y.im = add2(mul2(pk2(v.y, v.w), sg), aIm[jb][q]);
-                                    st_ps(slot, y);
+                                    yv[jb][q].re = add2(mul2(pk2(v.x, v.z), sg), aRe[jb][q]);
+                                    yv[jb][q].im = add2(mul2(pk2(v.y, v.w), sg), aIm[jb][q]);
                                 }
                         } else {
 #pragma unroll
-                            for (int jb = 0; jb < kJBC; ++jb) {
-                                const int j = tid + jo0 + jb * kOT;
+                            for (int jb = 0; jb < kJBC; ++jb)
 #pragma unroll
                                 for (int q = 0; q < NP; ++q) {
-                                    ps y = ld_ps(Yp[q] + j);
-                                    y.re = add2(y.re, aRe[jb][q]);
-                                    y.im = add2(y.im, aIm[jb][q]);
-                                    st_ps(Yp[q] + j, y);
+                                    const ps y = ld_ps(Yp[q] + tid + jo0 + jb * kOT);
+                                    yv[jb][q].re = add2(y.re, aRe[jb][q]);
+                                    yv[jb][q].im = add2(y.im, aIm[jb][q]);
                                 }
+                        }
+                        if (rx0_fused) {
+                            // one output block per frame and one rx pair: this thread holds the four inputs
+                            // tid + i fft/4 of butterfly `tid` of the rx FFT's first stage -> straight into W
+                            if constexpr (kFuseRx0) {
+                                ps y0, y1, y2, y3;
+                                bfly4<false>(yv[0][0], yv[1][0], yv[2][0], yv[3][0], y0, y1, y2, y3);
+                                fft_store_stage0(W, tid, true, y0, y1, y2, y3);
                             }
+                        } else {
+#pragma unroll
+                            for (int jb = 0; jb < kJBC; ++jb)
+#pragma unroll
+                                for (int q = 0; q < NP; ++q) st_ps(Yp[q] + tid + jo0 + jb * kOT, yv[jb][q]);
                         }
                     }
                 }
@@ -604,10 +622,14 @@ ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const cx
                 }
             }   // tx pairs
 
-            // ---------------- F: paired FFT of every rx pair (rotating pool)
+            // ---------------- F: paired FFT of every rx pair (rotating pool).  When the last pass produces exactly
+            // the bins a detection thread owns, it is left to the detection phase (fft_last_pass, from registers).
+            constexpr int NU = (NR * NT <= 4) ? 4 : 2;
+            const bool fuse_last = fft_last_fusable(p.lg, NU);
 #pragma unroll
             for (int q = 0; q < NP; ++q) {
-                float4 *res = fft_stockham_pair<false>(Yp[q], W, tw, fft, p.lg);
+                float4 *res = rx0_fused ? fft_stockham_pair<false>(W, Yp[q], tw, fft, p.lg, 1, fuse_last)
+                                        : fft_stockham_pair<false>(Yp[q], W, tw, fft, p.lg, 0, fuse_last);
                 if (res != Yp[q]) { W = Yp[q]; Yp[q] = res; }
             }
 
@@ -616,7 +638,6 @@ ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const cx
             // taps are summed per residue class d mod NU (host-sorted runs in the class order 0, 2, 1, 3:
             // OfdmP::cls_*, so that the classes mod 2 are contiguous too) and the class sums are combined by an
             // NU-point DFT.  NU = 4 when the 4 x NT x NP packed accumulators fit the register budget, else 2.
-            constexpr int NU = (NR * NT <= 4) ? 4 : 2;
             const int kstride = fft / NU;
             uint8_t *hat_fs = idx_hat ? idx_hat + size_t(frame) * p.n_data + size_t(s) * p.used * NT : nullptr;
             cx<T> *eq_fs = eq_out ? eq_out + size_t(frame) * p.n_data + size_t(s) * p.used * NT : nullptr;
@@ -674,6 +695,17 @@ ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const cx
                             Hc[1][t][q] = e - o;
                         }
                 }
+                // received bins of the NU subcarriers: the last FFT pass from registers, or plain loads
+                ps Yv[NP][NU];
+#pragma unroll
+                for (int qq = 0; qq < NP; ++qq) {
+                    if (fuse_last) {
+                        fft_last_pass<NU>(Yp[qq], tw, fft, p.lg, k0, Yv[qq]);
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < NU; ++u) Yv[qq][u] = ld_ps(Yp[qq] + k0 + u * kstride);
+                    }
+                }
                 // detection of the NU bins: branch-free arithmetic first (independent double chains of the bins
                 // overlap), then demap / count / store under the bin's validity predicate
                 cx<T> z[NU][NT];
@@ -690,9 +722,11 @@ ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const cx
                             upk2(Hc[u][t][qq].re, H[2 * qq][t].re, H[2 * qq + 1][t].re);
                             upk2(Hc[u][t][qq].im, H[2 * qq][t].im, H[2 * qq + 1][t].im);
                         }
-                        const float4 v = Yp[qq][k];
-                        y[2 * qq] = {rx_scale * v.x, rx_scale * v.z};
-                        y[2 * qq + 1] = {rx_scale * v.y, rx_scale * v.w};
+                        float yr0, yr1, yi0, yi1;
+                        upk2(Yv[qq][u].re, yr0, yr1);
+                        upk2(Yv[qq][u].im, yi0, yi1);
+                        y[2 * qq] = {rx_scale * yr0, rx_scale * yi0};
+                        y[2 * qq + 1] = {rx_scale * yr1, rx_scale * yi1};
                     }
                     if constexpr (NT == 2) {
                         // closed-form 2x2 (H^H H + s2 I)^-1 H^H y in double; 1/det by one Newton step on the float
