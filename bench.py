@@ -460,14 +460,25 @@ def main():
         "e2e": e2e, "gpu_launches": launches, "clocks": sampler.summary(), "counters": final,
     }
     if wname == DEFAULT:
-        # the real bound of this kernel is instruction issue: instructions per frame come from the
-        # committed ncu capture (profiles/ofdm_tdl_pair_2x2_r01_ncu_metrics.csv), the rate is live
-        wi = 277186414 / 5920.0
-        sm_mhz = line["clocks"].get("sm_mhz") or 1965.0
-        peak_wi = 148 * 4 * sm_mhz * 1e6
-        line["issue"] = {"warp_inst_per_unit": wi, "achieved_warp_inst_per_s": value / world * wi,
-                         "peak_warp_inst_per_s": peak_wi, "frac": value / world * wi / peak_wi,
-                         "source": "ncu smsp__inst_executed.sum, profiles/ofdm_tdl_pair_2x2_r01_ncu_metrics.csv"}
+        # the real bound of this kernel is instruction issue: instructions and DRAM bytes per frame come from
+        # the committed ncu --set full capture of the same kernel (profiles/headline_kernel_ncu.json), scaled
+        # to this launch's unit count; the rate is live
+        try:
+            cap = json.load(open(os.path.join(ROOT, 'profiles', 'headline_kernel_ncu.json')))
+        except Exception:
+            cap = None
+        if cap:
+            wi = float(cap['warp_inst_per_unit'])
+            sm_mhz = line["clocks"].get("sm_mhz") or 1965.0
+            peak_wi = 148 * 4 * sm_mhz * 1e6
+            line["roofline"]["traffic"] = cap['dram_bytes_per_unit'] * R
+            line["roofline"]["traffic_note"] = ("dram__bytes_read.sum + dram__bytes_write.sum = %.0f B/frame in the ncu capture "
+                                                "(%d frames/launch) x %d frames of this launch; algorithmic %d B/frame"
+                                                % (cap['dram_bytes_per_unit'], cap['units_per_launch'], R, bytes_per_unit))
+            line["roofline"]["algorithmic_bytes"] = bytes_per_unit * R
+            line["issue"] = {"warp_inst_per_unit": wi, "achieved_warp_inst_per_s": value / world * wi,
+                             "peak_warp_inst_per_s": peak_wi, "frac": value / world * wi / peak_wi,
+                             "source": "ncu smsp__inst_executed.sum, profiles/headline_kernel_ncu.json"}
     if not args.no_cpu:
         n1 = cpu_sample_size(w)
         v1, dt1 = time_cpu(wname, 1, n1)
