@@ -238,7 +238,7 @@ def usable_cores():
 
 
 # ------------------------------------------------------------------ reference arm
-def run_reference(args, wname, w):
+def run_reference(args, wname, w, emit):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
@@ -262,7 +262,7 @@ def run_reference(args, wname, w):
             "e2e": {"value": value, "unit": "realizations/s", "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------ B200 arm
@@ -276,11 +276,21 @@ def main():
     ap.add_argument('--units', type=int, default=0, help='realizations per step per GPU (0 = workload default)')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     args = ap.parse_args()
+    # stdout carries exactly ONE JSON line: anything a library prints there (e.g. NCCL's version banner,
+    # seen on the multi-GPU boxes) is routed to stderr; emit() writes the line to the real stdout
+    sys.stdout.flush()
+    real_out = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.write(real_out, (json.dumps(line) + '\n').encode())
+
     wname, w = args.workload, dict(WORKLOADS[args.workload])
     if args.units:
         w['units'] = args.units
     if args.impl == 'reference':
-        return run_reference(args, wname, w)
+        return run_reference(args, wname, w, emit)
 
     import torch
     import torch.distributed as dist
@@ -484,7 +494,7 @@ def main():
         v1, dt1 = time_cpu(wname, 1, n1)
         line["cpu_baseline"] = {"value": v1, "unit": "realizations/s", "cores": 1, "kind": "port",
                                 "sample": "%d units of the same workload in %.1f s on 1 core (NumPy oracle port)" % (n1, dt1)}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
