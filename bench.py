@@ -275,6 +275,7 @@ def main():
     ap.add_argument('--workload', default=DEFAULT, choices=sorted(WORKLOADS))
     ap.add_argument('--units', type=int, default=0, help='realizations per step per GPU (0 = workload default)')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--quick', action='store_true', help='kernel A/B runs: skip the e2e and cpu_baseline legs')
     args = ap.parse_args()
     # stdout carries exactly ONE JSON line: anything a library prints there (e.g. NCCL's version banner,
     # seen on the multi-GPU boxes) is routed to stderr; emit() writes the line to the real stdout
@@ -403,7 +404,7 @@ def main():
 
     # e2e: host buffers -> H2D -> kernel -> D2H through the C entry point (wall clock incl. sync)
     e2e = None
-    if e2e_call is not None:
+    if e2e_call is not None and not args.quick:
         for _ in range(2):
             e2e_call()
         if world > 1:
@@ -489,7 +490,7 @@ def main():
             line["issue"] = {"warp_inst_per_unit": wi, "achieved_warp_inst_per_s": value / world * wi,
                              "peak_warp_inst_per_s": peak_wi, "frac": value / world * wi / peak_wi,
                              "source": "ncu smsp__inst_executed.sum, profiles/headline_kernel_ncu.json"}
-    if not args.no_cpu:
+    if not (args.no_cpu or args.quick):
         n1 = cpu_sample_size(w)
         v1, dt1 = time_cpu(wname, 1, n1)
         line["cpu_baseline"] = {"value": v1, "unit": "realizations/s", "cores": 1, "kind": "port",
