@@ -39,28 +39,48 @@ static int launch_one(const OfdmP &p, const Modem &m, const void *table, uint64_
     return e;
 }
 
-template <bool FUSED, int NR, int NT, bool QAMK>
-static int launch_pair_k(const OfdmP &p, const Modem &m, const void *table, uint64_t first_unit, int64_t n_units,
-                       const uint8_t *idx, const void *phi, const void *psi, const void *noise,
-                       uint8_t *idx_hat, void *eq_out, int64_t *counters, size_t smem, cudaStream_t st) {
-    auto kern = ofdm_tdl_pair_kernel<FUSED, NR, NT, QAMK>;
+// threads per CTA of the pair kernel for the big shapes (Nr Nt > 4: one CTA per SM, limited by shared
+// memory).  512 threads = 16 warps per SM instead of 8, but at 128 registers per thread the 4x4 detection
+// spills (388 B): measured on C5 -4 % in stream mode, +5 % with the fused RNG -> 256 stays the default
+// (-DB200_PAIR_BIG_KT=512 builds the variant).
+#ifndef B200_PAIR_BIG_KT
+#define B200_PAIR_BIG_KT 256
+#endif
+
+template <bool FUSED, int NR, int NT, bool QAMK, int KT>
+static int launch_pair_kt(const OfdmP &p, const Modem &m, const void *table, uint64_t first_unit, int64_t n_units,
+                          const uint8_t *idx, const void *phi, const void *psi, const void *noise,
+                          uint8_t *idx_hat, void *eq_out, int64_t *counters, size_t smem, cudaStream_t st) {
+    auto kern = ofdm_tdl_pair_kernel<FUSED, NR, NT, QAMK, KT>;
     int e = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)),
                        "cudaFuncSetAttribute(ofdm_tdl_pair_kernel)");
     if (e) return e;
     int dev = 0, sms = 148, occ = 1;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    e = check_cuda(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kOT, smem),
+    e = check_cuda(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, KT, smem),
                    "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
     if (e) return e;
     if (occ < 1) return -1;                       // does not fit: caller falls back to the generic kernel
     long long grid = (long long)sms * occ;
     if (grid > n_units) grid = n_units;
-    kern<<<int(grid), kOT, smem, st>>>(p, m, (const cx<float> *)table, first_unit, (long long)n_units, idx,
-                                       (const float *)phi, (const float *)psi, (const cx<float> *)noise,
-                                       idx_hat, (cx<float> *)eq_out, (unsigned long long *)counters);
+    kern<<<int(grid), KT, smem, st>>>(p, m, (const cx<float> *)table, first_unit, (long long)n_units, idx,
+                                      (const float *)phi, (const float *)psi, (const cx<float> *)noise,
+                                      idx_hat, (cx<float> *)eq_out, (unsigned long long *)counters);
     count_launch();
     return check_cuda(cudaGetLastError(), "ofdm_tdl_pair_kernel launch");
+}
+
+template <bool FUSED, int NR, int NT, bool QAMK>
+static int launch_pair_k(const OfdmP &p, const Modem &m, const void *table, uint64_t first_unit, int64_t n_units,
+                       const uint8_t *idx, const void *phi, const void *psi, const void *noise,
+                       uint8_t *idx_hat, void *eq_out, int64_t *counters, size_t smem, cudaStream_t st) {
+    constexpr int KTB = (NR * NT > 4) ? B200_PAIR_BIG_KT : kOT;
+    if constexpr (KTB != kOT) {
+        if ((p.fft & (KTB * kJBC - 1)) == 0)
+            return launch_pair_kt<FUSED, NR, NT, QAMK, KTB>(p, m, table, first_unit, n_units, idx, phi, psi, noise, idx_hat, eq_out, counters, smem, st);
+    }
+    return launch_pair_kt<FUSED, NR, NT, QAMK, kOT>(p, m, table, first_unit, n_units, idx, phi, psi, noise, idx_hat, eq_out, counters, smem, st);
 }
 
 template <bool FUSED, int NR, int NT>

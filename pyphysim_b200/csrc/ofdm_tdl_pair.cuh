@@ -243,8 +243,8 @@ __device__ __forceinline__ void ray_moments_f32(cx<float> (&a)[4], const float *
 
 // QAMK: the modem kind is square Gray QAM at compile time (the slicer is inlined, the table-search / PSK paths
 // are not even in the binary: ~10 % less code in a kernel whose hot path does not fit the instruction cache)
-template <bool FUSED, int NR, int NT, bool QAMK>
-__global__ void __launch_bounds__(kOT, (NR * NT <= 4) ? 3 : 1)
+template <bool FUSED, int NR, int NT, bool QAMK, int KT = kOT>
+__global__ void __launch_bounds__(KT, (NR * NT <= 4) ? 3 : 1)
 ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const cx<float> *__restrict__ tab_g,
                      uint64_t first_unit, long long n_units, const uint8_t *__restrict__ idx_g,
                      const float *__restrict__ phi_g, const float *__restrict__ psi_g,
@@ -272,21 +272,21 @@ ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const cx
     T *ph_phi = (T *)take(sizeof(T) * p.P4);
     T *ph_psi = (T *)take(sizeof(T) * p.P4);
 
-    for (int i = tid; i < fft; i += kOT) {
+    for (int i = tid; i < fft; i += KT) {
         double s, c;
         sincospi(-2.0 * double(i) / double(fft), &s, &c);
         tw[i] = {T(c), T(s)};
     }
     fill_compact_twiddles(tw, fft);
     if (m.kind != B200PHY_MODEM_BPSK)
-        for (int k = tid; k < m.M; k += kOT) tab[k] = tab_g[k];
+        for (int k = tid; k < m.M; k += KT) tab[k] = tab_g[k];
     __syncthreads();
 
     unsigned sym_err = 0, bit_err = 0;
     const T sigma = T(p.sigma), tx_scale = T(p.tx_scale), rx_scale = T(p.rx_scale);
     const int n_items = p.n_taps * NR * 2;           // (tap, rx, t in pair)
     int G = 1;
-    while (G < 16 && (G * 2) * n_items <= kOT) G *= 2;
+    while (G < 16 && (G * 2) * n_items <= KT) G *= 2;
     const int sub = tid & (G - 1);
     const int ostride = p.n_taps * NR * NT;
     const double wts = p.w0 * p.Ts1, wt0 = p.w0 * p.t0;
@@ -298,31 +298,31 @@ ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const cx
     // pair's (still unused) accumulator buffer at frame start and merged in the FIR epilogue.
     // The data symbols of the next frame (8 B per thread and 2048 symbols) wait in registers instead.
     constexpr int kPre = (NR * NT <= 4) ? 1 : NT;
-    const bool pf = !FUSED && p.n_sym == 1 && (p.n_data & 7) == 0 && p.n_data <= 8 * kOT * kPre &&
+    const bool pf = !FUSED && p.n_sym == 1 && (p.n_data & 7) == 0 && p.n_data <= 8 * KT * kPre &&
                     (reinterpret_cast<uintptr_t>(idx_g) & 7) == 0;
     const bool pf16 = pf && (p.P & 3) == 0 && aligned16(phi_g) && aligned16(psi_g);
     const bool apipe = !FUSED;
     // rx FFT stage 0 straight from the FIR accumulators (one rx pair, one tx pair, one output block per frame)
     constexpr bool kFuseRx0 = (NP == 1 && TP == 1 && kJBC == 4);
-    const bool rx0_fused = kFuseRx0 && fft == kOT * kJBC;
+    const bool rx0_fused = kFuseRx0 && fft == KT * kJBC;
     uint2 idx_pre[kPre];
     auto prefetch = [&](long long f) {
         const T *gp = phi_g + size_t(f) * p.P, *gq = psi_g + size_t(f) * p.P;
         if (pf16) {
-            for (int i = tid; i < (p.P >> 2); i += kOT) {
+            for (int i = tid; i < (p.P >> 2); i += KT) {
                 cp_async<16>(ph_phi + 4 * i, gp + 4 * i);
                 cp_async<16>(ph_psi + 4 * i, gq + 4 * i);
             }
         } else {
-            for (int i = tid; i < p.P; i += kOT) {
+            for (int i = tid; i < p.P; i += KT) {
                 cp_async<4>(ph_phi + i, gp + i);
                 cp_async<4>(ph_psi + i, gq + i);
             }
         }
 #pragma unroll
         for (int u = 0; u < kPre; ++u)
-            if (tid + u * kOT < (p.n_data >> 3))
-                idx_pre[u] = __ldg(reinterpret_cast<const uint2 *>(idx_g + size_t(f) * p.n_data) + tid + u * kOT);
+            if (tid + u * KT < (p.n_data >> 3))
+                idx_pre[u] = __ldg(reinterpret_cast<const uint2 *>(idx_g + size_t(f) * p.n_data) + tid + u * KT);
     };
     if constexpr (!FUSED) {
         if (pf && blockIdx.x < n_units) prefetch(blockIdx.x);
@@ -338,7 +338,7 @@ ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const cx
 
         // ---- phases of all rays of this frame -> shared memory
         if constexpr (FUSED) {
-            for (int b = tid; b < (p.P4 >> 2); b += kOT) {
+            for (int b = tid; b < (p.P4 >> 2); b += KT) {
                 const uint4 b1 = rng_block(p.seed, STREAM_CHANNEL, unit, uint64_t(b));
                 const uint4 b2 = rng_block(p.seed, STREAM_CHANNEL, unit, uint64_t((p.P4 >> 2) + b));
 #pragma unroll
@@ -351,17 +351,17 @@ ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const cx
             cp_async_wait<0>();                      // prefetched during the previous frame (visible after the barrier below)
 #pragma unroll
             for (int u = 0; u < kPre; ++u)
-                if (tid + u * kOT < (p.n_data >> 3)) reinterpret_cast<uint2 *>(dsym)[tid + u * kOT] = idx_pre[u];
+                if (tid + u * KT < (p.n_data >> 3)) reinterpret_cast<uint2 *>(dsym)[tid + u * KT] = idx_pre[u];
         } else {
             const T *gp = phi_g + size_t(frame) * p.P, *gq = psi_g + size_t(frame) * p.P;
-            for (int i0 = tid; i0 < p.P; i0 += 4 * kOT) {
+            for (int i0 = tid; i0 < p.P; i0 += 4 * KT) {
                 T a[4], b[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u)
-                    if (i0 + u * kOT < p.P) { a[u] = __ldg(gp + i0 + u * kOT); b[u] = __ldg(gq + i0 + u * kOT); }
+                    if (i0 + u * KT < p.P) { a[u] = __ldg(gp + i0 + u * KT); b[u] = __ldg(gq + i0 + u * KT); }
 #pragma unroll
                 for (int u = 0; u < 4; ++u)
-                    if (i0 + u * kOT < p.P) { ph_phi[i0 + u * kOT] = a[u]; ph_psi[i0 + u * kOT] = b[u]; }
+                    if (i0 + u * KT < p.P) { ph_phi[i0 + u * KT] = a[u]; ph_psi[i0 + u * KT] = b[u]; }
             }
         }
 
@@ -372,7 +372,7 @@ ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const cx
                 const int w0 = s * p.used * NT, cnt = p.used * NT;
                 if constexpr (FUSED) {
                     const int b0 = w0 >> 2, b1 = (w0 + cnt - 1) >> 2;
-                    for (int b = b0 + tid; b <= b1; b += kOT) {
+                    for (int b = b0 + tid; b <= b1; b += KT) {
                         const uint4 blk = rng_block(p.seed, STREAM_DATA, unit, uint64_t(b));
 #pragma unroll
                         for (int l = 0; l < 4; ++l) {
@@ -385,15 +385,15 @@ ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const cx
                     if ((cnt & 3) == 0 && ((frame * p.n_data + w0) & 3) == 0) {
                         const uint32_t *s4 = reinterpret_cast<const uint32_t *>(src);
                         uint32_t *d4 = reinterpret_cast<uint32_t *>(dsym);
-                        for (int i = tid; i < (cnt >> 2); i += kOT) d4[i] = __ldg(s4 + i);
+                        for (int i = tid; i < (cnt >> 2); i += KT) d4[i] = __ldg(s4 + i);
                     } else {
-                        for (int i = tid; i < cnt; i += kOT) dsym[i] = src[i];
+                        for (int i = tid; i < cnt; i += KT) dsym[i] = src[i];
                     }
                 }
                 const int m0 = n_s + cp;
                 if constexpr (FUSED) {
                     const int pr0 = m0 >> 1, npr = ((m0 + fft - 1) >> 1) - pr0 + 1;
-                    for (int it = tid; it < NR * npr; it += kOT) {
+                    for (int it = tid; it < NR * npr; it += KT) {
                         const int r = it / npr, pr = pr0 + it % npr;
                         const uint4 blk = rng_block(p.seed, STREAM_NOISE, unit, uint64_t(r) * (p.row >> 1) + pr);
                         const int j = 2 * pr - m0;
@@ -410,7 +410,7 @@ ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const cx
                     for (int q = 0; q < NP; ++q) {
                         const cx<T> *s0 = noise_g + (size_t(frame) * NR + 2 * q) * rowlen + m0, *s1 = s0 + rowlen;
                         cx<T> *raw = reinterpret_cast<cx<T> *>(Yp[q]);
-                        for (int j = tid; j < fft; j += kOT) {
+                        for (int j = tid; j < fft; j += KT) {
                             cp_async<8>(raw + 2 * j, s0 + j);
                             cp_async<8>(raw + 2 * j + 1, s1 + j);
                         }
@@ -421,15 +421,15 @@ ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const cx
 #pragma unroll
                     for (int q = 0; q < NP; ++q) {
                         const cx<T> *s0 = noise_g + (size_t(frame) * NR + 2 * q) * rowlen + m0, *s1 = s0 + rowlen;
-                        for (int j0 = tid; j0 < fft; j0 += 4 * kOT) {
+                        for (int j0 = tid; j0 < fft; j0 += 4 * KT) {
                             cx<T> v0[4], v1[4];
 #pragma unroll
                             for (int u = 0; u < 4; ++u)
-                                if (j0 + u * kOT < fft) { v0[u] = load_stream(s0 + j0 + u * kOT); v1[u] = load_stream(s1 + j0 + u * kOT); }
+                                if (j0 + u * KT < fft) { v0[u] = load_stream(s0 + j0 + u * KT); v1[u] = load_stream(s1 + j0 + u * KT); }
 #pragma unroll
                             for (int u = 0; u < 4; ++u)
-                                if (j0 + u * kOT < fft)
-                                    Yp[q][j0 + u * kOT] = make_float4(sigma * v0[u].re, sigma * v1[u].re, sigma * v0[u].im, sigma * v1[u].im);
+                                if (j0 + u * KT < fft)
+                                    Yp[q][j0 + u * KT] = make_float4(sigma * v0[u].re, sigma * v1[u].re, sigma * v0[u].im, sigma * v1[u].im);
                         }
                     }
                 }
@@ -442,7 +442,7 @@ ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const cx
                 // the mapped symbols never touch shared memory.  Also the ISI tail of the previous symbol.
                 float4 *in = in_w ? W : body;
                 float4 *other = in_w ? body : W;
-                for (int j = tid; j < (fft >> 2); j += kOT) {
+                for (int j = tid; j < (fft >> 2); j += KT) {
                     ps v[4];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
@@ -458,10 +458,10 @@ ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const cx
                     bfly4<true>(v[0], v[1], v[2], v[3], y0, y1, y2, y3);
                     fft_store_stage0(other, j, true, y0, y1, y2, y3);
                 }
-                for (int i = tid; i < mem; i += kOT)
+                for (int i = tid; i < mem; i += KT)
                     E2[i] = (s > 0) ? tails[tp * mem + i] : make_float4(0.f, 0.f, 0.f, 0.f);
                 // ---------------- C: ray setup, items (tap, rx, t in pair), G lanes per item
-                for (int it0 = 0; it0 < n_items; it0 += kOT / G) {
+                for (int it0 = 0; it0 < n_items; it0 += KT / G) {
                     const int it = it0 + tid / G;
                     const bool act = it < n_items;
                     const int l = act ? it / (NR * 2) : 0;
@@ -525,12 +525,12 @@ ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const cx
                 {
                     const float tau0 = float(tid) - 0.5f * float(fft - 1);
                     const float4 *xb = E2 + mem + cp + tid;
-                    for (int jo0 = 0; jo0 < fft; jo0 += kOT * kJBC) {
+                    for (int jo0 = 0; jo0 < fft; jo0 += KT * kJBC) {
                         u64 aRe[kJBC][NP], aIm[kJBC][NP];
                         float tauv[kJBC];
 #pragma unroll
                         for (int jb = 0; jb < kJBC; ++jb) {
-                            tauv[jb] = tau0 + float(jo0 + jb * kOT);
+                            tauv[jb] = tau0 + float(jo0 + jb * KT);
 #pragma unroll
                             for (int q = 0; q < NP; ++q) { aRe[jb][q] = 0ull; aIm[jb][q] = 0ull; }
                         }
@@ -543,7 +543,7 @@ ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const cx
                                 const float4 *xl = xb + (jo0 - p.delays[l]);
                                 float4 x4[kJBC];
 #pragma unroll
-                                for (int jb = 0; jb < kJBC; ++jb) x4[jb] = xl[jb * kOT];
+                                for (int jb = 0; jb < kJBC; ++jb) x4[jb] = xl[jb * KT];
 #pragma unroll
                                 for (int tt = 0; tt < 2; ++tt) {
                                     u64 cR[NP][NO], cI[NP][NO];
@@ -586,7 +586,7 @@ ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const cx
                             for (int jb = 0; jb < kJBC; ++jb)
 #pragma unroll
                                 for (int q = 0; q < NP; ++q) {
-                                    const float4 v = Yp[q][tid + jo0 + jb * kOT];       // (n0.re, n0.im, n1.re, n1.im)
+                                    const float4 v = Yp[q][tid + jo0 + jb * KT];       // (n0.re, n0.im, n1.re, n1.im)
                                     // rounded product then sum: bit-identical to the fused-RNG path
                                     yv[jb][q].re = add2(mul2(pk2(v.x, v.z), sg), aRe[jb][q]);
                                     yv[jb][q].im = add2(mul2(pk2(v.y, v.w), sg), aIm[jb][q]);
@@ -596,7 +596,7 @@ ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const cx
                             for (int jb = 0; jb < kJBC; ++jb)
 #pragma unroll
                                 for (int q = 0; q < NP; ++q) {
-                                    const ps y = ld_ps(Yp[q] + tid + jo0 + jb * kOT);
+                                    const ps y = ld_ps(Yp[q] + tid + jo0 + jb * KT);
                                     yv[jb][q].re = add2(y.re, aRe[jb][q]);
                                     yv[jb][q].im = add2(y.im, aIm[jb][q]);
                                 }
@@ -613,13 +613,13 @@ ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const cx
 #pragma unroll
                             for (int jb = 0; jb < kJBC; ++jb)
 #pragma unroll
-                                for (int q = 0; q < NP; ++q) st_ps(Yp[q] + tid + jo0 + jb * kOT, yv[jb][q]);
+                                for (int q = 0; q < NP; ++q) st_ps(Yp[q] + tid + jo0 + jb * KT, yv[jb][q]);
                         }
                     }
                 }
                 __syncthreads();
                 if (p.n_sym > 1) {
-                    for (int i = tid; i < mem; i += kOT) tails[tp * mem + i] = E2[S + i];
+                    for (int i = tid; i < mem; i += KT) tails[tp * mem + i] = E2[S + i];
                     __syncthreads();
                 }
             }   // tx pairs
@@ -644,7 +644,7 @@ ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const cx
             uint8_t *hat_fs = idx_hat ? idx_hat + size_t(frame) * p.n_data + size_t(s) * p.used * NT : nullptr;
             cx<T> *eq_fs = eq_out ? eq_out + size_t(frame) * p.n_data + size_t(s) * p.used * NT : nullptr;
             const bool hat_vec = (reinterpret_cast<uintptr_t>(hat_fs) & (NT - 1)) == 0;
-            for (int k0 = tid; k0 < kstride; k0 += kOT) {
+            for (int k0 = tid; k0 < kstride; k0 += KT) {
                 ps Hc[NU][NT][NP];
 #pragma unroll
                 for (int u = 0; u < NU; ++u)
