@@ -214,8 +214,9 @@ __device__ __forceinline__ bool fft_last_fusable(int lg, int NU) {
 template <bool O3>
 __device__ __forceinline__ void ray_moments_f32(cx<float> (&a)[4], const float *pphi, const float *ppsi, int first,
                                                 int L, int step, int stride, float eps, float wts) {
-    // psi / pi as a two-float product (hi + lo of 1/pi), reduced by the nearest even integer before the
-    // small terms are added: the phase reaches sincospif with ~6e-8 half-turn error, like the double path
+    // psi / pi as a two-float product (hi + lo of 1/pi), reduced by the nearest half-integer k / 2 (exactly)
+    // before the small terms are added: the phase reaches the polynomials with ~6e-8 half-turn error, like
+    // the double path
     constexpr float kInvPi = 0.31830987334251404f, kInvPiLo = 1.284127663345183e-08f;
     const float eps_pi = eps * kInvPi;
 #pragma unroll 2
@@ -229,7 +230,12 @@ __device__ __forceinline__ void ray_moments_f32(cx<float> (&a)[4], const float *
         e = fmaf(psi, kInvPiLo, e);
         e = fmaf(eps_pi, cphi, e);
         float sn, cs;
+#ifdef B200_LIB_SINCOSPI
         sincospif((t - 2.0f * rintf(0.5f * t)) + e, &sn, &cs);
+#else
+        const float k = rintf(t + t);            // t in [0, 2): k in 0..4
+        sincospi_kf(k, fmaf(k, -0.5f, t) + e, &sn, &cs);
+#endif
         a[0].re += cs;                      a[0].im += sn;
         a[1].re = fmaf(-d1, sn, a[1].re);   a[1].im = fmaf(d1, cs, a[1].im);
         a[2].re = fmaf(d2, cs, a[2].re);    a[2].im = fmaf(d2, sn, a[2].im);
