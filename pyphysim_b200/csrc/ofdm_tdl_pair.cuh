@@ -455,8 +455,10 @@ ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const cx
                         const int q = pos_of(j + i * (fft >> 2), fft, p.used, p.half);
                         v[i] = {0ull, 0ull};
                         if (q >= 0) {
-                            const cx<T> s0 = map_symbol<T>(m, tab, dsym[q * NT + 2 * tp]);
-                            const cx<T> s1 = map_symbol<T>(m, tab, dsym[q * NT + 2 * tp + 1]);
+                            // the two antennas' symbols of a subcarrier are adjacent (and NT is even): one 16-bit load
+                            const unsigned two = *reinterpret_cast<const uint16_t *>(dsym + q * NT + 2 * tp);
+                            const cx<T> s0 = map_symbol<T>(m, tab, int(two & 0xffu));
+                            const cx<T> s1 = map_symbol<T>(m, tab, int(two >> 8));
                             v[i] = {pk2(tx_scale * s0.re, tx_scale * s1.re), pk2(tx_scale * s0.im, tx_scale * s1.im)};
                         }
                     }
@@ -659,8 +661,12 @@ ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const cx
 #pragma unroll
                         for (int q = 0; q < NP; ++q) Hc[u][t][q] = {0ull, 0ull};
                 auto tap_sum = [&](ps (&acc)[NT][NP], int j0, int j1) {
-#ifdef B200_HK_NOUNROLL
+#if defined(B200_HK_UNROLL1)
 #pragma unroll 1
+#elif defined(B200_HK_UNROLL2)
+#pragma unroll 2
+#elif defined(B200_HK_UNROLL4)
+#pragma unroll 4
 #endif
                     for (int j = j0; j < j1; ++j) {
                         const cx<T> w = tw[(k0 * p.cls_delay[j]) & (fft - 1)];
@@ -751,7 +757,10 @@ ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const cx
                             cmac_conj(v1, h1, yr);
                         }
                         const double det = a * bb - norm2(c);
-                        double rd = double(__frcp_rn(float(det)));
+                        // MUFU.RCP seed (2^-23 relative) + one Newton step in double: 1e-14 relative
+                        float rdf;
+                        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rdf) : "f"(float(det)));
+                        double rd = double(rdf);
                         rd = rd * fma(-det, rd, 2.0);
                         const double g = rd * p.snt;
                         z[u][0] = {T(g * (bb * v0.re - (c.re * v1.re + c.im * v1.im))), T(g * (bb * v0.im - (c.re * v1.im - c.im * v1.re)))};
