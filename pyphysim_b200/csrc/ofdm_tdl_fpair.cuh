@@ -9,7 +9,8 @@
 
 namespace b200phy {
 
-template <bool FUSED, bool QAMK>
+// LGF: compile-time log2(fft) of a full-band frame (see ofdm_tdl_pair_kernel), 0 = run-time shape
+template <bool FUSED, bool QAMK, int LGF = 0>
 __global__ void __launch_bounds__(kOT, 3)
 ofdm_tdl_fpair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const cx<float> *__restrict__ tab_g,
                       uint64_t first_unit, long long n_pairs, const uint8_t *__restrict__ idx_g,
@@ -21,7 +22,9 @@ ofdm_tdl_fpair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const c
     if (QAMK) m.kind = B200PHY_MODEM_QAM;      // compile-time kind (see ofdm_tdl_pair_kernel)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x;
-    const int fft = p.fft, S = p.S, mem = p.mem, cp = p.cp;
+    const int fft = LGF ? (1 << LGF) : p.fft, lg = LGF ? LGF : p.lg;
+    const int used = LGF ? fft : p.used, half = LGF ? (fft >> 1) : p.half;
+    const int S = p.S, mem = p.mem, cp = p.cp;
 
     unsigned char *sp = smem_raw;
     auto take = [&](size_t bytes) { unsigned char *r = sp; sp += (bytes + 15) & ~size_t(15); return r; };
@@ -33,7 +36,7 @@ ofdm_tdl_fpair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const c
     float4 *tails = (float4 *)take(p.n_sym > 1 ? sizeof(float4) * mem : 0);
     u64 *coef = (u64 *)take(sizeof(u64) * p.n_taps * 4 * 2);            // [tap][order][re|im]
     cx<T> *tab = (cx<T> *)take(sizeof(cx<T>) * m.M);
-    uint8_t *dsym = (uint8_t *)take(2 * p.used);                        // [frame lane][used]
+    uint8_t *dsym = (uint8_t *)take(2 * used);                        // [frame lane][used]
     T *ph_phi = (T *)take(sizeof(T) * 2 * p.P4);                        // [frame lane][P4]
     T *ph_psi = (T *)take(sizeof(T) * 2 * p.P4);
 
@@ -122,7 +125,7 @@ ofdm_tdl_fpair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const c
             const int n_s = s * S;
             // ---------------- P0: data symbols of both frames, noise into Y
             {
-                const int w0 = s * p.used, cnt = p.used;
+                const int w0 = s * used, cnt = used;
                 if constexpr (FUSED) {
                     const int b0 = w0 >> 2, nb = ((w0 + cnt - 1) >> 2) - b0 + 1;
                     for (int it = tid; it < 2 * nb; it += kOT) {
@@ -131,14 +134,14 @@ ofdm_tdl_fpair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const c
 #pragma unroll
                         for (int l = 0; l < 4; ++l) {
                             const int w = 4 * b + l - w0;
-                            if (w >= 0 && w < cnt) dsym[ln * p.used + w] = uint8_t(lane_of(blk, l) >> (32 - m.bits));
+                            if (w >= 0 && w < cnt) dsym[ln * used + w] = uint8_t(lane_of(blk, l) >> (32 - m.bits));
                         }
                     }
                 } else if (!pf) {
 #pragma unroll
                     for (int ln = 0; ln < 2; ++ln) {
                         const uint8_t *src = idx_g + size_t(frame + ln) * p.n_data + w0;
-                        for (int i = tid; i < cnt; i += kOT) dsym[ln * p.used + i] = src[i];
+                        for (int i = tid; i < cnt; i += kOT) dsym[ln * used + i] = src[i];
                     }
                 }
                 const int m0 = n_s + cp;
@@ -184,11 +187,11 @@ ofdm_tdl_fpair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const c
             float4 *in = in_w ? W : body;
             float4 *other = in_w ? body : W;
             for (int k = tid; k < fft; k += kOT) {
-                const int q = pos_of(k, fft, p.used, p.half);
+                const int q = pos_of(k, fft, used, half);
                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (q >= 0) {
                     const cx<T> s0 = map_symbol<T>(m, tab, dsym[q]);
-                    const cx<T> s1 = map_symbol<T>(m, tab, dsym[p.used + q]);
+                    const cx<T> s1 = map_symbol<T>(m, tab, dsym[used + q]);
                     v = make_float4(tx_scale * s0.re, tx_scale * s1.re, tx_scale * s0.im, tx_scale * s1.im);
                 }
                 in[k] = v;
@@ -243,7 +246,7 @@ ofdm_tdl_fpair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const c
                 }
             }
             // ---------------- B: paired IFFT, cyclic prefix, ISI tail
-            fft_stockham_pair<true>(in, other, tw, fft, p.lg);
+            fft_stockham_pair<true>(in, other, tw, fft, lg);
             if constexpr (!FUSED) {                   // ray setup done: the phase buffers are free
                 if (pf && pr + gridDim.x < n_pairs) prefetch(2 * (pr + gridDim.x));
                 cp_async_commit();
@@ -327,7 +330,7 @@ ofdm_tdl_fpair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const c
 
             // ---------------- F: paired FFT of both frames
             {
-                float4 *res = fft_stockham_pair<false>(Y, W, tw, fft, p.lg);
+                float4 *res = fft_stockham_pair<false>(Y, W, tw, fft, lg);
                 if (res != Y) { W = Y; Y = res; }
             }
 
@@ -360,7 +363,7 @@ ofdm_tdl_fpair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const c
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const int k = k0 + u * kstride;
-                    const int q = pos_of(k, fft, p.used, p.half);
+                    const int q = pos_of(k, fft, used, half);
                     if (q < 0) continue;
                     const float4 yv = Y[k];
                     float hr0, hr1, hi0, hi1;
@@ -371,11 +374,11 @@ ofdm_tdl_fpair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const c
                         const cx<T> y = ln ? mk<T>(rx_scale * yv.y, rx_scale * yv.w) : mk<T>(rx_scale * yv.x, rx_scale * yv.z);
                         const cx<T> H = ln ? mk<T>(hr1, hi1) : mk<T>(hr0, hi0);
                         const cx<T> z = cdiv(y, H);
-                        const int a = dsym[ln * p.used + q];
+                        const int a = dsym[ln * used + q];
                         const int e = demap_symbol<T>(m, tab, z);
                         sym_err += (e != a);
                         bit_err += __popc(e ^ a);
-                        const size_t o = size_t(frame + ln) * p.n_data + size_t(s * p.used + q);
+                        const size_t o = size_t(frame + ln) * p.n_data + size_t(s * used + q);
                         if (idx_hat) idx_hat[o] = uint8_t(e);
                         if (eq_out) eq_out[o] = z;
                     }

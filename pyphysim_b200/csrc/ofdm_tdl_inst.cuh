@@ -6,6 +6,10 @@
 
 namespace b200phy {
 
+#ifndef B200_PAIR_STATIC_SHAPE
+#define B200_PAIR_STATIC_SHAPE 1
+#endif
+
 template <typename T, bool FUSED, int NR, int NT, bool WSG>
 static int launch_one(const OfdmP &p, const Modem &m, const void *table, uint64_t first_unit,
                       int64_t n_units, const uint8_t *idx, const void *phi, const void *psi,
@@ -47,11 +51,11 @@ static int launch_one(const OfdmP &p, const Modem &m, const void *table, uint64_
 #define B200_PAIR_BIG_KT 256
 #endif
 
-template <bool FUSED, int NR, int NT, bool QAMK, int KT>
+template <bool FUSED, int NR, int NT, bool QAMK, int KT, int LGF>
 static int launch_pair_kt(const OfdmP &p, const Modem &m, const void *table, uint64_t first_unit, int64_t n_units,
                           const uint8_t *idx, const void *phi, const void *psi, const void *noise,
                           uint8_t *idx_hat, void *eq_out, int64_t *counters, size_t smem, cudaStream_t st) {
-    auto kern = ofdm_tdl_pair_kernel<FUSED, NR, NT, QAMK, KT>;
+    auto kern = ofdm_tdl_pair_kernel<FUSED, NR, NT, QAMK, KT, LGF>;
     int e = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)),
                        "cudaFuncSetAttribute(ofdm_tdl_pair_kernel)");
     if (e) return e;
@@ -71,6 +75,9 @@ static int launch_pair_kt(const OfdmP &p, const Modem &m, const void *table, uin
     return check_cuda(cudaGetLastError(), "ofdm_tdl_pair_kernel launch");
 }
 
+// compile-time frame shape of the headline config (full band, fft 1024, 2x2); everything else takes the
+// run-time-shape instantiation
+
 template <bool FUSED, int NR, int NT, bool QAMK>
 static int launch_pair_k(const OfdmP &p, const Modem &m, const void *table, uint64_t first_unit, int64_t n_units,
                        const uint8_t *idx, const void *phi, const void *psi, const void *noise,
@@ -78,9 +85,17 @@ static int launch_pair_k(const OfdmP &p, const Modem &m, const void *table, uint
     constexpr int KTB = (NR * NT > 4) ? B200_PAIR_BIG_KT : kOT;
     if constexpr (KTB != kOT) {
         if ((p.fft & (KTB * kJBC - 1)) == 0)
-            return launch_pair_kt<FUSED, NR, NT, QAMK, KTB>(p, m, table, first_unit, n_units, idx, phi, psi, noise, idx_hat, eq_out, counters, smem, st);
+            return launch_pair_kt<FUSED, NR, NT, QAMK, KTB, 0>(p, m, table, first_unit, n_units, idx, phi, psi, noise, idx_hat, eq_out, counters, smem, st);
     }
-    return launch_pair_kt<FUSED, NR, NT, QAMK, kOT>(p, m, table, first_unit, n_units, idx, phi, psi, noise, idx_hat, eq_out, counters, smem, st);
+#if B200_PAIR_STATIC_SHAPE
+    // measured: +12 % on the 2x2 headline; the 4-antenna kernels (1 CTA/SM, 170-220 registers) get slower
+    // with the fully unrolled FFT stages (C5 -12 %), so they keep the run-time shape
+    if constexpr (NR * NT <= 4) {
+        if (p.fft == 1024 && p.used == p.fft)
+            return launch_pair_kt<FUSED, NR, NT, QAMK, kOT, 10>(p, m, table, first_unit, n_units, idx, phi, psi, noise, idx_hat, eq_out, counters, smem, st);
+    }
+#endif
+    return launch_pair_kt<FUSED, NR, NT, QAMK, kOT, 0>(p, m, table, first_unit, n_units, idx, phi, psi, noise, idx_hat, eq_out, counters, smem, st);
 }
 
 template <bool FUSED, int NR, int NT>
@@ -92,11 +107,11 @@ static int launch_pair(const OfdmP &p, const Modem &m, const void *table, uint64
     return launch_pair_k<FUSED, NR, NT, false>(p, m, table, first_unit, n_units, idx, phi, psi, noise, idx_hat, eq_out, counters, smem, st);
 }
 
-template <bool FUSED, bool QAMK>
-static int launch_fpair_k(const OfdmP &p, const Modem &m, const void *table, uint64_t first_unit, int64_t n_pairs,
+template <bool FUSED, bool QAMK, int LGF>
+static int launch_fpair_kl(const OfdmP &p, const Modem &m, const void *table, uint64_t first_unit, int64_t n_pairs,
                         const uint8_t *idx, const void *phi, const void *psi, const void *noise,
                         uint8_t *idx_hat, void *eq_out, int64_t *counters, size_t smem, cudaStream_t st) {
-    auto kern = ofdm_tdl_fpair_kernel<FUSED, QAMK>;
+    auto kern = ofdm_tdl_fpair_kernel<FUSED, QAMK, LGF>;
     int e = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)),
                        "cudaFuncSetAttribute(ofdm_tdl_fpair_kernel)");
     if (e) return e;
@@ -114,6 +129,17 @@ static int launch_fpair_k(const OfdmP &p, const Modem &m, const void *table, uin
                                        idx_hat, (cx<float> *)eq_out, (unsigned long long *)counters);
     count_launch();
     return check_cuda(cudaGetLastError(), "ofdm_tdl_fpair_kernel launch");
+}
+
+template <bool FUSED, bool QAMK>
+static int launch_fpair_k(const OfdmP &p, const Modem &m, const void *table, uint64_t first_unit, int64_t n_pairs,
+                        const uint8_t *idx, const void *phi, const void *psi, const void *noise,
+                        uint8_t *idx_hat, void *eq_out, int64_t *counters, size_t smem, cudaStream_t st) {
+#if B200_PAIR_STATIC_SHAPE
+    if (p.fft == 1024 && p.used == p.fft)
+        return launch_fpair_kl<FUSED, QAMK, 10>(p, m, table, first_unit, n_pairs, idx, phi, psi, noise, idx_hat, eq_out, counters, smem, st);
+#endif
+    return launch_fpair_kl<FUSED, QAMK, 0>(p, m, table, first_unit, n_pairs, idx, phi, psi, noise, idx_hat, eq_out, counters, smem, st);
 }
 
 template <bool FUSED>

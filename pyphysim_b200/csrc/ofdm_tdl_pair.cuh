@@ -249,7 +249,10 @@ __device__ __forceinline__ void ray_moments_f32(cx<float> (&a)[4], const float *
 
 // QAMK: the modem kind is square Gray QAM at compile time (the slicer is inlined, the table-search / PSK paths
 // are not even in the binary: ~10 % less code in a kernel whose hot path does not fit the instruction cache)
-template <bool FUSED, int NR, int NT, bool QAMK, int KT = kOT>
+// LGF: log2(fft) at compile time for the full-band shapes the BASELINE configs use (used == fft; 10 or 11),
+// 0 = run-time shape.  With the size known every FFT stage loop, stage-kind branch and bin -> position map
+// folds to constants (one trip per loop, immediate offsets).
+template <bool FUSED, int NR, int NT, bool QAMK, int KT = kOT, int LGF = 0>
 __global__ void __launch_bounds__(KT, (NR * NT <= 4) ? 3 : 1)
 ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const cx<float> *__restrict__ tab_g,
                      uint64_t first_unit, long long n_units, const uint8_t *__restrict__ idx_g,
@@ -262,7 +265,9 @@ ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const cx
     if (QAMK) m.kind = B200PHY_MODEM_QAM;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x;
-    const int fft = p.fft, S = p.S, mem = p.mem, cp = p.cp;
+    const int fft = LGF ? (1 << LGF) : p.fft, lg = LGF ? LGF : p.lg;
+    const int used = LGF ? fft : p.used, half = LGF ? (fft >> 1) : p.half;
+    const int S = p.S, mem = p.mem, cp = p.cp;
 
     unsigned char *sp = smem_raw;
     auto take = [&](size_t bytes) { unsigned char *r = sp; sp += (bytes + 15) & ~size_t(15); return r; };
@@ -274,7 +279,7 @@ ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const cx
     float4 *tails = (float4 *)take(p.n_sym > 1 ? sizeof(float4) * TP * mem : 0);
     u64 *coef = (u64 *)take(sizeof(u64) * p.n_taps * NP * 2 * 4 * 2);   // [tap][rx pair][t in pair][order][re|im]
     cx<T> *tab = (cx<T> *)take(sizeof(cx<T>) * m.M);
-    uint8_t *dsym = (uint8_t *)take(NT * p.used);
+    uint8_t *dsym = (uint8_t *)take(NT * used);
     T *ph_phi = (T *)take(sizeof(T) * p.P4);
     T *ph_psi = (T *)take(sizeof(T) * p.P4);
 
@@ -375,7 +380,7 @@ ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const cx
             const int n_s = s * S;
             // ---------------- P0: data symbols, noise into the rx pair buffers
             {
-                const int w0 = s * p.used * NT, cnt = p.used * NT;
+                const int w0 = s * used * NT, cnt = used * NT;
                 if constexpr (FUSED) {
                     const int b0 = w0 >> 2, b1 = (w0 + cnt - 1) >> 2;
                     for (int b = b0 + tid; b <= b1; b += KT) {
@@ -452,7 +457,7 @@ ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const cx
                     ps v[4];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        const int q = pos_of(j + i * (fft >> 2), fft, p.used, p.half);
+                        const int q = pos_of(j + i * (fft >> 2), fft, used, half);
                         v[i] = {0ull, 0ull};
                         if (q >= 0) {
                             // the two antennas' symbols of a subcarrier are adjacent (and NT is even): one 16-bit load
@@ -521,7 +526,7 @@ ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const cx
                     }
                 }
                 // ---------------- B: remaining IFFT passes (end in E2.body); the last one also writes the cyclic prefix
-                fft_stockham_pair<true>(other, in, tw, fft, p.lg, 1, false, cp);
+                fft_stockham_pair<true>(other, in, tw, fft, lg, 1, false, cp);
                 if constexpr (!FUSED) {
                     if (tp == TP - 1) {              // last ray setup done: the phase buffers are free
                         if (pf && frame + gridDim.x < n_units) prefetch(frame + gridDim.x);
@@ -635,11 +640,11 @@ ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const cx
             // ---------------- F: paired FFT of every rx pair (rotating pool).  When the last pass produces exactly
             // the bins a detection thread owns, it is left to the detection phase (fft_last_pass, from registers).
             constexpr int NU = (NR * NT <= 4) ? 4 : 2;
-            const bool fuse_last = fft_last_fusable(p.lg, NU);
+            const bool fuse_last = fft_last_fusable(lg, NU);
 #pragma unroll
             for (int q = 0; q < NP; ++q) {
-                float4 *res = rx0_fused ? fft_stockham_pair<false>(W, Yp[q], tw, fft, p.lg, 1, fuse_last)
-                                        : fft_stockham_pair<false>(Yp[q], W, tw, fft, p.lg, 0, fuse_last);
+                float4 *res = rx0_fused ? fft_stockham_pair<false>(W, Yp[q], tw, fft, lg, 1, fuse_last)
+                                        : fft_stockham_pair<false>(Yp[q], W, tw, fft, lg, 0, fuse_last);
                 if (res != Yp[q]) { W = Yp[q]; Yp[q] = res; }
             }
 
@@ -649,8 +654,8 @@ ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const cx
             // OfdmP::cls_*, so that the classes mod 2 are contiguous too) and the class sums are combined by an
             // NU-point DFT.  NU = 4 when the 4 x NT x NP packed accumulators fit the register budget, else 2.
             const int kstride = fft / NU;
-            uint8_t *hat_fs = idx_hat ? idx_hat + size_t(frame) * p.n_data + size_t(s) * p.used * NT : nullptr;
-            cx<T> *eq_fs = eq_out ? eq_out + size_t(frame) * p.n_data + size_t(s) * p.used * NT : nullptr;
+            uint8_t *hat_fs = idx_hat ? idx_hat + size_t(frame) * p.n_data + size_t(s) * used * NT : nullptr;
+            cx<T> *eq_fs = eq_out ? eq_out + size_t(frame) * p.n_data + size_t(s) * used * NT : nullptr;
             const bool hat_vec = (reinterpret_cast<uintptr_t>(hat_fs) & (NT - 1)) == 0;
             for (int k0 = tid; k0 < kstride; k0 += KT) {
                 ps Hc[NU][NT][NP];
@@ -714,7 +719,7 @@ ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const cx
 #pragma unroll
                 for (int qq = 0; qq < NP; ++qq) {
                     if (fuse_last) {
-                        fft_last_pass<NU>(Yp[qq], tw, fft, p.lg, k0, Yv[qq]);
+                        fft_last_pass<NU>(Yp[qq], tw, fft, lg, k0, Yv[qq]);
                     } else {
 #pragma unroll
                         for (int u = 0; u < NU; ++u) Yv[qq][u] = ld_ps(Yp[qq] + k0 + u * kstride);
@@ -727,7 +732,7 @@ ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const cx
 #pragma unroll
                 for (int u = 0; u < NU; ++u) {
                     const int k = k0 + u * kstride;
-                    qv[u] = pos_of(k, fft, p.used, p.half);
+                    qv[u] = pos_of(k, fft, used, half);
                     cx<T> H[NR][NT], y[NR];
 #pragma unroll
                     for (int qq = 0; qq < NP; ++qq) {
