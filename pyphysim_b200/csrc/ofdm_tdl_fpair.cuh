@@ -246,7 +246,7 @@ ofdm_tdl_fpair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const c
                 }
             }
             // ---------------- B: paired IFFT, cyclic prefix, ISI tail
-            fft_stockham_pair<true>(in, other, tw, fft, lg);
+            fft_stockham_pair<true, LGF ? kOT : 0>(in, other, tw, fft, lg);
             if constexpr (!FUSED) {                   // ray setup done: the phase buffers are free
                 if (pf && pr + gridDim.x < n_pairs) prefetch(2 * (pr + gridDim.x));
                 cp_async_commit();
@@ -330,7 +330,7 @@ ofdm_tdl_fpair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const c
 
             // ---------------- F: paired FFT of both frames
             {
-                float4 *res = fft_stockham_pair<false>(Y, W, tw, fft, lg);
+                float4 *res = fft_stockham_pair<false, LGF ? kOT : 0>(Y, W, tw, fft, lg);
                 if (res != Y) { W = Y; Y = res; }
             }
 

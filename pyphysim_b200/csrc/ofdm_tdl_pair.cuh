@@ -128,18 +128,22 @@ __device__ __forceinline__ void fft_load_stage(const float4 *src, const cx<float
 // stage-0 output layout for first_stage == 1) and ping-pongs with `b`; returns the buffer holding the result,
 // synchronised.  cp > 0 (never with skip_last): the last pass also writes the cyclic prefix, i.e. output
 // element o >= N - cp goes to index o - N of the result buffer as well.
-template <bool INV>
-__device__ float4 *fft_stockham_pair(float4 *a, float4 *b, const cx<float> *tw, int N, int lg, int first_stage = 0,
-                                     bool skip_last = false, int cp = 0) {
+// NTHR: CTA size at compile time (0 = blockDim.x).  With N, lg and NTHR known the stage loop unrolls into
+// straight-line stages (one butterfly per thread for N = 4 NTHR, constant strides, no stage-kind branches).
+template <bool INV, int NTHR = 0>
+__device__ __forceinline__ float4 *fft_stockham_pair(float4 *a, float4 *b, const cx<float> *tw, int N, int lg,
+                                                     int first_stage = 0, bool skip_last = false, int cp = 0) {
     float4 *src = a, *dst = b;
     const bool sw = fft_sw(N, lg);
     const int nst = lg >> 1, q = N >> 2;
+    const int nthr = NTHR ? NTHR : int(blockDim.x);
     const int last4 = (lg & 1) ? nst : (skip_last ? nst - 1 : nst);       // radix-4 stages to run: [first, last4)
     int Ns = 1 << (2 * first_stage);
+#pragma unroll
     for (int st = first_stage; st < last4; ++st) {
         __syncthreads();
         const bool wcp = cp > 0 && !(lg & 1) && st == nst - 1;
-        for (int j = threadIdx.x; j < q; j += blockDim.x) {
+        for (int j = threadIdx.x; j < q; j += nthr) {
             ps y0, y1, y2, y3;
             if (st == 0) {
                 bfly4<INV>(ld_ps(src + j), ld_ps(src + j + q), ld_ps(src + j + 2 * q), ld_ps(src + j + 3 * q), y0, y1, y2, y3);
@@ -167,7 +171,7 @@ __device__ float4 *fft_stockham_pair(float4 *a, float4 *b, const cx<float> *tw, 
     if ((lg & 1) && !skip_last) {
         __syncthreads();
         const int h = N >> 1;
-        for (int j = threadIdx.x; j < h; j += blockDim.x) {
+        for (int j = threadIdx.x; j < h; j += nthr) {
             const int k = j & (Ns - 1);
             const cx<float> w = tw[k];
             const ps v0 = ld_ps(src + j), v1 = mul_w(ld_ps(src + j + h), w.re, INV ? -w.im : w.im);
@@ -526,7 +530,7 @@ ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const cx
                     }
                 }
                 // ---------------- B: remaining IFFT passes (end in E2.body); the last one also writes the cyclic prefix
-                fft_stockham_pair<true>(other, in, tw, fft, lg, 1, false, cp);
+                fft_stockham_pair<true, LGF ? KT : 0>(other, in, tw, fft, lg, 1, false, cp);
                 if constexpr (!FUSED) {
                     if (tp == TP - 1) {              // last ray setup done: the phase buffers are free
                         if (pf && frame + gridDim.x < n_units) prefetch(frame + gridDim.x);
@@ -643,8 +647,8 @@ ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const cx
             const bool fuse_last = fft_last_fusable(lg, NU);
 #pragma unroll
             for (int q = 0; q < NP; ++q) {
-                float4 *res = rx0_fused ? fft_stockham_pair<false>(W, Yp[q], tw, fft, lg, 1, fuse_last)
-                                        : fft_stockham_pair<false>(Yp[q], W, tw, fft, lg, 0, fuse_last);
+                float4 *res = rx0_fused ? fft_stockham_pair<false, LGF ? KT : 0>(W, Yp[q], tw, fft, lg, 1, fuse_last)
+                                        : fft_stockham_pair<false, LGF ? KT : 0>(Yp[q], W, tw, fft, lg, 0, fuse_last);
                 if (res != Yp[q]) { W = Yp[q]; Yp[q] = res; }
             }
 
