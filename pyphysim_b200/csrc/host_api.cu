@@ -30,6 +30,19 @@ static int ctx_init(HostCtx &c) {
     int e = check_cuda(cudaGetDevice(&dev), "cudaGetDevice");
     if (e) return e;
     if (c.dev == dev) return B200PHY_OK;
+    if (c.dev >= 0) {
+        // the caller switched devices (one process per GPU is the normal deployment): release what lives on
+        // the previous device before building the context on the current one
+        cudaSetDevice(c.dev);
+        for (auto &s : c.slot) {
+            if (s.st) { cudaStreamSynchronize(s.st); cudaStreamDestroy(s.st); s.st = nullptr; }
+            for (int i = 0; i < 5; ++i) { if (s.buf[i]) cudaFree(s.buf[i]); s.buf[i] = nullptr; s.cap[i] = 0; }
+            if (s.counters) { cudaFree(s.counters); s.counters = nullptr; }
+        }
+        if (c.table) { cudaFree(c.table); c.table = nullptr; }
+        c.dev = -1;
+        if ((e = check_cuda(cudaSetDevice(dev), "cudaSetDevice"))) return e;
+    }
     for (auto &s : c.slot) {
         if ((e = check_cuda(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking), "cudaStreamCreate"))) return e;
         if ((e = check_cuda(cudaMalloc((void **)&s.counters, 4 * sizeof(long long)), "cudaMalloc(counters)"))) return e;
