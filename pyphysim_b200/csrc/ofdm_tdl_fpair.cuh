@@ -60,6 +60,8 @@ ofdm_tdl_fpair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const c
     const double wts = p.w0 * p.Ts1, wt0 = p.w0 * p.t0;
     const bool in_w = p.ifft_in_w != 0;
     const bool o3 = p.porder == 3;
+    // rx FFT stage 0 straight from the FIR accumulators (one output block per frame)
+    const bool rx0_fused = (kJBC == 4) && fft == kOT * kJBC;
 
     // stream-mode input pipeline, as in ofdm_tdl_pair.cuh: next pair's phases by LDGSTS during the FIR, its
     // data symbols in two registers, raw noise rows into the (unused) rx buffer at frame start
@@ -183,19 +185,28 @@ ofdm_tdl_fpair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const c
             }
             __syncthreads();
 
-            // ---------------- A: map + scatter (lanes = frames)
+            // ---------------- A: map + scatter (lanes = frames), fused with IFFT stage 0: the thread that maps bins
+            // j + i fft/4 owns butterfly j of the first (twiddle-free) radix-4 stage (as in ofdm_tdl_pair_kernel)
             float4 *in = in_w ? W : body;
             float4 *other = in_w ? body : W;
-            for (int k = tid; k < fft; k += kOT) {
-                const int q = pos_of(k, fft, used, half);
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (q >= 0) {
-                    const cx<T> s0 = map_symbol<T>(m, tab, dsym[q]);
-                    const cx<T> s1 = map_symbol<T>(m, tab, dsym[used + q]);
-                    v = make_float4(tx_scale * s0.re, tx_scale * s1.re, tx_scale * s0.im, tx_scale * s1.im);
+            for (int j = tid; j < (fft >> 2); j += kOT) {
+                ps v[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int q = pos_of(j + i * (fft >> 2), fft, used, half);
+                    v[i] = {0ull, 0ull};
+                    if (q >= 0) {
+                        const cx<T> s0 = map_symbol<T>(m, tab, dsym[q]);
+                        const cx<T> s1 = map_symbol<T>(m, tab, dsym[used + q]);
+                        v[i] = {pk2(tx_scale * s0.re, tx_scale * s1.re), pk2(tx_scale * s0.im, tx_scale * s1.im)};
+                    }
                 }
-                in[k] = v;
+                ps y0, y1, y2, y3;
+                bfly4<true>(v[0], v[1], v[2], v[3], y0, y1, y2, y3);
+                fft_store_stage0(other, j, true, y0, y1, y2, y3);
             }
+            for (int i = tid; i < mem; i += kOT)
+                E2[i] = (s > 0) ? tails[i] : make_float4(0.f, 0.f, 0.f, 0.f);
             // ---------------- C: ray setup, items (tap, frame lane)
             for (int it0 = 0; it0 < n_items; it0 += kOT / G) {
                 const int it = it0 + tid / G;
@@ -240,21 +251,17 @@ ofdm_tdl_fpair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const c
                     cq[0] = a0.re; cq[2] = a0.im; cq[4] = a1.re; cq[6] = a1.im;
                     cq[8] = a2.re; cq[10] = a2.im; cq[12] = a3.re; cq[14] = a3.im;
                     const T m1 = T(p.mu[0][l]), m2 = T(p.mu[1][l]), m3 = T(p.mu[2][l]);
-                    T *gq = reinterpret_cast<T *>(gbar) + l * 4 + ln;
+                    T *gq = reinterpret_cast<T *>(gbar) + p.cls_pos[l] * 4 + ln;      // class-sorted (see G)
                     gq[0] = a0.re + m1 * a1.re + m2 * a2.re + m3 * a3.re;
                     gq[2] = a0.im + m1 * a1.im + m2 * a2.im + m3 * a3.im;
                 }
             }
-            // ---------------- B: paired IFFT, cyclic prefix, ISI tail
-            fft_stockham_pair<true, LGF ? kOT : 0>(in, other, tw, fft, lg);
+            // ---------------- B: remaining IFFT passes (end in E2.body); the last one also writes the cyclic prefix
+            fft_stockham_pair<true, LGF ? kOT : 0>(other, in, tw, fft, lg, 1, false, cp);
             if constexpr (!FUSED) {                   // ray setup done: the phase buffers are free
                 if (pf && pr + gridDim.x < n_pairs) prefetch(2 * (pr + gridDim.x));
                 cp_async_commit();
             }
-            for (int i = tid; i < cp; i += kOT) E2[mem + i] = body[fft - cp + i];
-            for (int i = tid; i < mem; i += kOT)
-                E2[i] = (s > 0) ? tails[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-            __syncthreads();
 
             // ---------------- D: FIR, lane-wise: y += g(tau) * x with all four partial products packed
             {
@@ -297,28 +304,37 @@ ofdm_tdl_fpair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const c
                         }
                     };
                     if (o3) taps(std::true_type{}); else taps(std::false_type{});
+                    ps yv[kJBC];
                     if (!FUSED && apipe) {
                         // this thread's raw noise slots have landed: y = sigma * noise + FIR, re-laid as pairs
                         cp_async_wait<1>();
                         const u64 sg = pk2(sigma, sigma);
 #pragma unroll
                         for (int jb = 0; jb < kJBC; ++jb) {
-                            float4 *slot = Y + tid + jo0 + jb * kOT;
-                            const float4 v = *slot;   // (nA.re, nA.im, nB.re, nB.im)
-                            ps y;                     // rounded product then sum: bit-identical to the fused-RNG path
-                            y.re = add2(mul2(pk2(v.x, v.z), sg), sub2(aRR[jb], aII[jb]));
-                            y.im = add2(mul2(pk2(v.y, v.w), sg), add2(aRI[jb], aIR[jb]));
-                            st_ps(slot, y);
+                            const float4 v = Y[tid + jo0 + jb * kOT];   // (nA.re, nA.im, nB.re, nB.im)
+                            // rounded product then sum: bit-identical to the fused-RNG path
+                            yv[jb].re = add2(mul2(pk2(v.x, v.z), sg), sub2(aRR[jb], aII[jb]));
+                            yv[jb].im = add2(mul2(pk2(v.y, v.w), sg), add2(aRI[jb], aIR[jb]));
                         }
                     } else {
 #pragma unroll
                         for (int jb = 0; jb < kJBC; ++jb) {
-                            const int j = tid + jo0 + jb * kOT;
-                            ps y = ld_ps(Y + j);
-                            y.re = add2(y.re, sub2(aRR[jb], aII[jb]));
-                            y.im = add2(y.im, add2(aRI[jb], aIR[jb]));
-                            st_ps(Y + j, y);
+                            const ps y = ld_ps(Y + tid + jo0 + jb * kOT);
+                            yv[jb].re = add2(y.re, sub2(aRR[jb], aII[jb]));
+                            yv[jb].im = add2(y.im, add2(aRI[jb], aIR[jb]));
                         }
+                    }
+                    if (rx0_fused) {
+                        // one output block per frame: this thread holds the four inputs tid + i fft/4 of butterfly
+                        // `tid` of the rx FFT's first stage -> straight into W
+                        if constexpr (kJBC == 4) {
+                            ps y0, y1, y2, y3;
+                            bfly4<false>(yv[0], yv[1], yv[2], yv[3], y0, y1, y2, y3);
+                            fft_store_stage0(W, tid, true, y0, y1, y2, y3);
+                        }
+                    } else {
+#pragma unroll
+                        for (int jb = 0; jb < kJBC; ++jb) st_ps(Y + tid + jo0 + jb * kOT, yv[jb]);
                     }
                 }
             }
@@ -328,30 +344,36 @@ ofdm_tdl_fpair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const c
                 __syncthreads();
             }
 
-            // ---------------- F: paired FFT of both frames
+            // ---------------- F: paired FFT of both frames; when the last pass yields exactly the 4 bins of a detection
+            // thread it is left to the detection phase (fft_last_pass, from registers)
+            const bool fuse_last = fft_last_fusable(lg, 4);
             {
-                float4 *res = fft_stockham_pair<false, LGF ? kOT : 0>(Y, W, tw, fft, lg);
+                float4 *res = rx0_fused ? fft_stockham_pair<false, LGF ? kOT : 0>(W, Y, tw, fft, lg, 1, fuse_last)
+                                        : fft_stockham_pair<false, LGF ? kOT : 0>(Y, W, tw, fft, lg, 0, fuse_last);
                 if (res != Y) { W = Y; Y = res; }
             }
 
-            // ---------------- G: H_k (both frames packed), one-tap equaliser, demap, count
+            // ---------------- G: H_k (both frames packed), one-tap equaliser, demap, count.  The taps are summed per
+            // residue class of their delay mod 4 (class-sorted runs OfdmP::cls_*, order 0, 2, 1, 3) and the class
+            // sums combined by a 4-point DFT, as in ofdm_tdl_pair_kernel.
             const int kstride = fft >> 2;
             for (int k0 = tid; k0 < kstride; k0 += kOT) {
                 ps Sc[4];
 #pragma unroll
                 for (int c = 0; c < 4; ++c) Sc[c] = {0ull, 0ull};
-                for (int l = 0; l < p.n_taps; ++l) {
-                    const int d = p.delays[l];
-                    const cx<T> w = tw[(k0 * d) & (fft - 1)];
-                    const ps g = {gbar[l * 2], gbar[l * 2 + 1]};
-                    const ps pr2 = mul_w(g, w.re, w.im);
-                    switch (d & 3) {
-                        case 0: Sc[0] = Sc[0] + pr2; break;
-                        case 1: Sc[1] = Sc[1] + pr2; break;
-                        case 2: Sc[2] = Sc[2] + pr2; break;
-                        default: Sc[3] = Sc[3] + pr2; break;
+                auto tap_sum = [&](ps &acc, int j0, int j1) {
+                    for (int j = j0; j < j1; ++j) {
+                        const cx<T> w = tw[(k0 * p.cls_delay[j]) & (fft - 1)];
+                        const u64 WR = pk2(w.re, w.re), WI = pk2(w.im, w.im), NWI = pk2(-w.im, -w.im);
+                        const ps g = {gbar[j * 2], gbar[j * 2 + 1]};
+                        acc.re = fma2(g.im, NWI, fma2(g.re, WR, acc.re));
+                        acc.im = fma2(g.im, WR, fma2(g.re, WI, acc.im));
                     }
-                }
+                };
+                tap_sum(Sc[0], p.cls_start[0], p.cls_start[1]);
+                tap_sum(Sc[2], p.cls_start[1], p.cls_start[2]);
+                tap_sum(Sc[1], p.cls_start[2], p.cls_start[3]);
+                tap_sum(Sc[3], p.cls_start[3], p.cls_start[4]);
                 ps Hk[4];
                 {
                     const ps a0 = Sc[0] + Sc[2], a1 = Sc[0] - Sc[2], a2 = Sc[1] + Sc[3], a3 = Sc[1] - Sc[3];
@@ -360,18 +382,26 @@ ofdm_tdl_fpair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const c
                     Hk[2] = a0 - a2;
                     Hk[3] = {sub2(a1.re, a3.im), add2(a1.im, a3.re)};     // a1 + j a3
                 }
+                ps Yv[4];
+                if (fuse_last) {
+                    fft_last_pass<4>(Y, tw, fft, lg, k0, Yv);
+                } else {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) Yv[u] = ld_ps(Y + k0 + u * kstride);
+                }
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const int k = k0 + u * kstride;
                     const int q = pos_of(k, fft, used, half);
                     if (q < 0) continue;
-                    const float4 yv = Y[k];
-                    float hr0, hr1, hi0, hi1;
+                    float yr0, yr1, yi0, yi1, hr0, hr1, hi0, hi1;
+                    upk2(Yv[u].re, yr0, yr1);
+                    upk2(Yv[u].im, yi0, yi1);
                     upk2(Hk[u].re, hr0, hr1);
                     upk2(Hk[u].im, hi0, hi1);
 #pragma unroll
                     for (int ln = 0; ln < 2; ++ln) {
-                        const cx<T> y = ln ? mk<T>(rx_scale * yv.y, rx_scale * yv.w) : mk<T>(rx_scale * yv.x, rx_scale * yv.z);
+                        const cx<T> y = ln ? mk<T>(rx_scale * yr1, rx_scale * yi1) : mk<T>(rx_scale * yr0, rx_scale * yi0);
                         const cx<T> H = ln ? mk<T>(hr1, hi1) : mk<T>(hr0, hi0);
                         const cx<T> z = cdiv(y, H);
                         const int a = dsym[ln * used + q];

@@ -201,7 +201,10 @@ def test_frame_pair_kernel_vs_generic_kernel(mod, M, fft, cp, nsym, n):
     draws = pair.draw(500, n)
     c_p, hat_p, eq_p = pair.run(n, first_unit=500, draws=draws, want_idx=True, want_eq=True)
     c_g, hat_g, eq_g = gen.run(n, first_unit=500, draws=draws, want_idx=True, want_eq=True)
-    assert_samples_close(_t(eq_p), _t(eq_g), 2e-5, 'frame-pair vs generic')
+    # two float32 kernels with different summation orders (class-sorted H_k, FFT passes fused through registers):
+    # 3e-5 of max(|ref|, rms) between them - the cp = 0 case (no cyclic prefix: ISI, equalised rms 4.6) sits at
+    # 2.1e-5 in its deepest fade; each kernel is held to the float64 oracle separately below
+    assert_samples_close(_t(eq_p), _t(eq_g), 3e-5, 'frame-pair vs generic')
     nbad = assert_decisions(_t(hat_p), _t(hat_g), cfg.modem, _t(eq_g).astype(complex), exact=False, eps=2e-3)
     assert abs(int(c_p[0]) - int(c_g[0])) <= nbad and c_p[2] == c_g[2] == n * nsym * fft
     c_f, hat_f = pair.run(n, first_unit=500, want_idx=True)
