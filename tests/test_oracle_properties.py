@@ -66,6 +66,7 @@ def test_static_channel_with_cp_is_one_tap_per_subcarrier(lg, ntaps, seed):
     (and its mean-taps restatement) rests on."""
     fft = 1 << lg
     rng = np.random.default_rng(seed)
+    ntaps = min(ntaps, fft // 4)
     delays = np.sort(rng.choice(np.arange(0, fft // 4), size=ntaps, replace=False))
     cp = int(delays[-1]) + int(rng.integers(0, 3))
     x = _cn(rng, fft)
