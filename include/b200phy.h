@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define B200PHY_VERSION 100
+#define B200PHY_VERSION 101
 
 enum { B200PHY_F32 = 0, B200PHY_F64 = 1 };
 
@@ -245,7 +245,11 @@ int b200phy_mmse_estimate(int dtype, const void *Y, const void *s, int s_per_uni
 /* ---- fused link ops (throughput path) ------------------------------------------
  * Each covers realizations/frames [first_unit, first_unit + n_units).  Draw arrays are
  * "stream mode" inputs; pass them all NULL for "fused mode" (in-kernel Philox).
- * idx_hat / dec_out are optional outputs (NULL to skip). */
+ * idx_hat / dec_out are optional outputs (NULL to skip).
+ * Alignment (vector loads): stream-mode arrays must start on their natural vector boundary — idx / idx_hat
+ * 4 bytes (2 for Alamouti), complex / real draw arrays 16 bytes for the flat SISO and Alamouti links and one
+ * element for the others — i.e. pass whole contiguous tensors, not slices at odd offsets; a misaligned
+ * pointer returns B200PHY_ERR_INVALID. */
 
 /* 1 symbol per realization: r = h*x + sqrt(noise_var)*n; r /= h
  * (notebooks/Transmission_with_Rayleigh_and_AWGN_channels.ipynb cell 8; rayleigh=0 is the AWGN
@@ -288,11 +292,17 @@ int b200phy_link_precoded(int dtype, const b200phy_modem *modem, int scheme, int
 /* OFDM over Jakes/TDL, SISO or Blast-MIMO (see b200phy_ofdm_tdl_params).
  * idx dev uint8[n][Nt*n_sym*used]; phi, psi dev real[n][L][n_taps][Nr][Nt];
  * noise dev complex[n][Nr][N+mem] (unit variance), N = n_sym*(fft+cp);
- * idx_hat dev uint8 like idx; eq_out dev complex[n][Nt*n_sym*used] (equalised symbols). */
+ * idx_hat dev uint8 like idx; eq_out dev complex[n][Nt*n_sym*used] (equalised symbols);
+ * rx_out dev complex[n][Nr][n_sym*used]: what OFDM.demodulate returns per rx antenna (ofdm.py:431-466),
+ * i.e. the samples BEFORE the equaliser / Blast.decode — the quantity the 1e-5 sample tolerance is held on. */
 int b200phy_link_ofdm_tdl(const b200phy_ofdm_tdl_params *p, const b200phy_modem *modem,
                           uint64_t first_unit, int64_t n_units, const uint8_t *idx, const void *phi,
                           const void *psi, const void *noise, uint8_t *idx_hat, void *eq_out,
-                          int64_t *counters, void *stream);
+                          void *rx_out, int64_t *counters, void *stream);
+
+/* Validates a parameter block exactly as b200phy_link_ofdm_tdl would (struct size, dtype, the OFDM.set_parameters
+ * checks of modulators/ofdm.py:75-90, tap / ray / antenna ranges, Jakes mode) without touching the device. */
+int b200phy_ofdm_tdl_check_params(const b200phy_ofdm_tdl_params *p);
 
 /* ---- draw dumps: write the fused-mode Philox draws in the stream-mode layouts, so the oracle can
  * consume literally the numbers the device used.  NULL outputs are skipped. */
@@ -307,13 +317,31 @@ int b200phy_draw_ofdm_tdl(const b200phy_ofdm_tdl_params *p, int bits, uint64_t f
 
 /* ---- host-buffer entry points (what a non-CUDA caller binds; `e2e` in bench.py) -------------
  * Same semantics as the device versions but every array is a HOST pointer (pinned memory makes the
- * copies asynchronous); the library stages chunks through its own device buffers, overlapping
- * H2D, compute and D2H on internal streams, and returns after the results are in host memory.
- * counters is host int64[4], accumulated. */
+ * copies asynchronous), and the constellation is passed as M (re, im) double pairs.
+ *   Monte Carlo mode — all draw arrays and idx_hat NULL: what one `_run_simulation` call of a
+ *   SimulationRunner needs (simulations/runner.py:1491-1517 merges only the counters).  One kernel over all
+ *   units; the parameters go in, 32 bytes of counters come back.
+ *   Stream mode — draw arrays and / or idx_hat given: the library stages ~64 MiB chunks through its own
+ *   device buffers, overlapping H2D, compute and D2H on two internal streams.
+ * Returns after the results are in host memory.  counters is host int64[4], accumulated.  Arguments are
+ * validated before anything is copied; on error nothing is left in flight. */
 int b200phy_link_siso_flat_host(int dtype, int modem_kind, int M, const double *table_re_im,
                                 int rayleigh, double noise_var, uint64_t seed, uint64_t first_unit,
                                 int64_t n_units, const uint8_t *idx, const void *h,
                                 const void *noise, uint8_t *idx_hat, int64_t *counters);
+/* simulate_mimo.py:68-142 with mimo.Alamouti / mimo.Blast / mimo.SVDMimo, GMDMimo, MRT (the device versions above) */
+int b200phy_link_alamouti_host(int dtype, int modem_kind, int M, const double *table_re_im, int Nr, int S,
+                               double noise_var, uint64_t seed, uint64_t first_unit, int64_t n_units,
+                               const uint8_t *idx, const void *H, const void *noise, uint8_t *idx_hat,
+                               int64_t *counters);
+int b200phy_link_blast_host(int dtype, int modem_kind, int M, const double *table_re_im, int Nr, int Nt, int S,
+                            double noise_var, double filter_noise_var, uint64_t seed, uint64_t first_unit,
+                            int64_t n_units, const uint8_t *idx, const void *H, const void *noise,
+                            uint8_t *idx_hat, int64_t *counters);
+int b200phy_link_precoded_host(int dtype, int modem_kind, int M, const double *table_re_im, int scheme, int Nr,
+                               int Nt, int S, double noise_var, double filter_noise_var, uint64_t seed,
+                               uint64_t first_unit, int64_t n_units, const uint8_t *idx, const void *H,
+                               const void *noise, uint8_t *idx_hat, int64_t *counters);
 int b200phy_link_ofdm_tdl_host(const b200phy_ofdm_tdl_params *p, int modem_kind, int M,
                                const double *table_re_im, uint64_t first_unit, int64_t n_units,
                                const uint8_t *idx, const void *phi, const void *psi,

@@ -144,7 +144,7 @@ class OfdmTdlConfig:
         return (self.L, ntaps, self.Nr, self.Nt) if self.mimo else (self.L, ntaps)
 
 
-def ofdm_tdl_frame(cfg, idx, phi, psi, noise, reference_equalizer=False, detail=False):
+def ofdm_tdl_frame(cfg, idx, phi, psi, noise, reference_equalizer=False, detail=False, per_subcarrier_loop=False):
     """One frame.  idx[n_data], phi/psi[cfg.phase_shape], noise[Nr, N+mem]
     (unit variance).  Returns idx_hat[n_data] (and intermediates if detail)."""
     m = cfg.modem
@@ -171,15 +171,27 @@ def ofdm_tdl_frame(cfg, idx, phi, psi, noise, reference_equalizer=False, detail=
         Hm = ofdm.mean_freq_response(taps, cfg.delays, cfg.fft, cfg.n_sym)  # [n_sym, fft, Nr, Nt]
         bins = ofdm.used_subcarrier_indexes(cfg.fft, cfg.used)
         Yg = Y.reshape(cfg.Nr, cfg.n_sym, cfg.used)
-        eq = np.empty(cfg.n_data, dtype=complex)
-        for sy in range(cfg.n_sym):
-            for q in range(cfg.used):
-                j = sy * cfg.used + q
-                eq[j * cfg.Nt:(j + 1) * cfg.Nt] = mimo.blast_decode(
-                    Yg[:, sy, q].reshape(cfg.Nr, 1), Hm[sy, bins[q]], cfg.filter_noise_var)
+        if per_subcarrier_loop:
+            # exactly how a caller of the reference would do it: one Blast object state per subcarrier
+            eq = np.empty(cfg.n_data, dtype=complex)
+            for sy in range(cfg.n_sym):
+                for q in range(cfg.used):
+                    j = sy * cfg.used + q
+                    eq[j * cfg.Nt:(j + 1) * cfg.Nt] = mimo.blast_decode(
+                        Yg[:, sy, q].reshape(cfg.Nr, 1), Hm[sy, bins[q]], cfg.filter_noise_var)
+        else:
+            # same LAPACK calls on the stack of all subcarriers (mimo.blast_receive_filter_batched)
+            Hk = Hm[:, bins]                                                 # [n_sym, used, Nr, Nt]
+            G = mimo.blast_receive_filter_batched(Hk.reshape(-1, cfg.Nr, cfg.Nt), cfg.filter_noise_var)
+            yk = np.moveaxis(Yg, 0, -1).reshape(-1, cfg.Nr, 1)               # [n_sym*used, Nr, 1]
+            eq = (G @ yk).reshape(-1)                                        # symbol j*Nt + t
     idx_hat = m.demodulate(eq)
     if detail:
-        return idx_hat, dict(tx=tx, h=h, rx=rx, Y=Y, Hm=Hm, eq=eq)
+        det = dict(tx=tx, h=h, rx=rx, Y=Y, Hm=Hm, eq=eq)
+        if cfg.mimo and not per_subcarrier_loop:
+            det['G'] = G                                                     # [n_sym*used, Nt, Nr]
+            det['Hk'] = Hk.reshape(-1, cfg.Nr, cfg.Nt)
+        return idx_hat, det
     return idx_hat
 
 

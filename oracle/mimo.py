@@ -37,6 +37,18 @@ def blast_decode(y, H, noise_var=0.0):
     return blast_receive_filter(H, noise_var).dot(y).reshape(-1, order='F')
 
 
+def blast_receive_filter_batched(H, noise_var=0.0):
+    """blast_receive_filter for a stack H[K, Nr, Nt] (one matrix per subcarrier).  np.linalg.solve / pinv on a
+    stack run the same LAPACK routine once per matrix, so every G[k] equals the per-matrix call
+    (tests/test_oracle_kat.py::test_blast_batched_equals_loop)."""
+    Hh = np.conj(np.swapaxes(H, -1, -2))
+    if noise_var > 0:
+        G = np.linalg.solve(Hh @ H + noise_var * np.eye(H.shape[-1]), Hh)
+    else:
+        G = np.linalg.pinv(H)
+    return G * math.sqrt(H.shape[-1])
+
+
 def alamouti_encode(s):
     """Alamouti.encode/_encode (mimo.py:1166-1214): [[s0, -s1*], [s1, s0*]] / sqrt(2)."""
     Ns = s.size

@@ -27,6 +27,10 @@ def _nvcc():
     return exe
 
 
+def have_nvcc():
+    return bool(shutil.which('nvcc')) or os.path.exists('/usr/local/cuda/bin/nvcc')
+
+
 def _sources():
     return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith('.cu'))
 

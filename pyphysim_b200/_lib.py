@@ -90,7 +90,7 @@ SIGNATURES = {
     'b200phy_mmse_estimate': (C.c_int, [C.c_int, _vp, _vp, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_double, _f64p,
                                         _vp, _vp]),
     'b200phy_link_ofdm_tdl': (C.c_int, [_PP, _MP, C.c_uint64, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp,
-                                        _vp, _vp]),
+                                        _vp, _vp, _vp]),
     'b200phy_draw_siso_flat': (C.c_int, [C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_int64, _vp, _vp,
                                          _vp, _vp]),
     'b200phy_draw_flat_mimo': (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
@@ -101,6 +101,15 @@ SIGNATURES = {
                                               _i64p]),
     'b200phy_link_ofdm_tdl_host': (C.c_int, [_PP, C.c_int, C.c_int, _f64p, C.c_uint64, C.c_int64, _vp,
                                              _vp, _vp, _vp, _vp, _i64p]),
+    'b200phy_ofdm_tdl_check_params': (C.c_int, [_PP]),
+    'b200phy_link_alamouti_host': (C.c_int, [C.c_int, C.c_int, C.c_int, _f64p, C.c_int, C.c_int, C.c_double,
+                                             C.c_uint64, C.c_uint64, C.c_int64, _vp, _vp, _vp, _vp, _i64p]),
+    'b200phy_link_blast_host': (C.c_int, [C.c_int, C.c_int, C.c_int, _f64p, C.c_int, C.c_int, C.c_int,
+                                          C.c_double, C.c_double, C.c_uint64, C.c_uint64, C.c_int64, _vp, _vp,
+                                          _vp, _vp, _i64p]),
+    'b200phy_link_precoded_host': (C.c_int, [C.c_int, C.c_int, C.c_int, _f64p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                             C.c_double, C.c_double, C.c_uint64, C.c_uint64, C.c_int64, _vp, _vp,
+                                             _vp, _vp, _i64p]),
 }
 
 _lib = None
@@ -119,9 +128,13 @@ def load():
     with _lock:
         if _lib is not None:
             return _lib
-        if not os.path.exists(LIB_PATH):
+        if 'B200PHY_LIB' not in os.environ:
+            # the .so is git-ignored but travels with snapshots: rebuild when csrc/ or include/ changed since it
+            # was built (source-digest check, a no-op when current).  Without nvcc (a pure runtime box) the
+            # shipped binary is used as is; b200phy_version / struct_size still guard the ABI.
             from . import _build
-            _build.build()
+            if not os.path.exists(LIB_PATH) or _build.have_nvcc():
+                _build.build()
         try:
             lib = C.CDLL(LIB_PATH)
         except OSError as e:                       # no silent fallback: this IS the product

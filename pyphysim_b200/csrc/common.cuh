@@ -153,6 +153,16 @@ int check_cuda(cudaError_t e, const char *what);
 void count_launch(int n = 1);
 int check_modem(const b200phy_modem *m, Modem *out);
 
+// Stream-mode kernels use vector loads / stores: a base pointer that is not aligned to `a` bytes (a sliced
+// tensor, an odd element offset) must be refused here, not fault inside the kernel.  NULL passes.
+inline int require_aligned(const void *ptr, size_t a, const char *name) {
+    if (ptr && (reinterpret_cast<uintptr_t>(ptr) & (a - 1))) {
+        set_error("%s must be %zu-byte aligned (got %p): pass a contiguous tensor from its first element", name, a, ptr);
+        return B200PHY_ERR_INVALID;
+    }
+    return B200PHY_OK;
+}
+
 #define B200_CHECK_LAUNCH(what)                                            \
     do {                                                                   \
         count_launch();                                                    \

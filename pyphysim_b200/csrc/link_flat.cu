@@ -468,6 +468,9 @@ int b200phy_link_siso_flat(int dtype, const b200phy_modem *modem, int rayleigh, 
         set_error("stream mode needs idx, noise%s together; fused mode needs all NULL", rayleigh ? ", h" : "");
         return B200PHY_ERR_INVALID;
     }
+    if ((e = require_aligned(idx, 4, "idx")) || (e = require_aligned(h, 16, "h")) || (e = require_aligned(noise, 16, "noise")) ||
+        (e = require_aligned(idx_hat, 4, "idx_hat")) || (e = require_aligned(dec_out, dtype == B200PHY_F32 ? 8 : 16, "dec_out")))
+        return e;
     if (n_units == 0) return B200PHY_OK;
     cudaStream_t st = (cudaStream_t)stream;
     return dtype == B200PHY_F32
@@ -486,6 +489,9 @@ int b200phy_link_alamouti(int dtype, const b200phy_modem *modem, int Nr, int S, 
     if (Nr < 1 || Nr > B200PHY_MAX_ANT) { set_error("Alamouti: Nr=%d must be in [1, %d]", Nr, B200PHY_MAX_ANT); return B200PHY_ERR_UNSUPPORTED; }
     if (S < 2 || (S & 1)) { set_error("Alamouti: number of symbols S=%d must be even", S); return B200PHY_ERR_INVALID; }
     if (!draws_consistent(idx, H, noise, true)) { set_error("stream mode needs idx, H, noise together"); return B200PHY_ERR_INVALID; }
+    if ((e = require_aligned(idx, 2, "idx")) || (e = require_aligned(H, 16, "H")) || (e = require_aligned(noise, 16, "noise")) ||
+        (e = require_aligned(idx_hat, 2, "idx_hat")) || (e = require_aligned(dec_out, dtype == B200PHY_F32 ? 8 : 16, "dec_out")))
+        return e;
     if (n_units == 0) return B200PHY_OK;
     cudaStream_t st = (cudaStream_t)stream;
     return dtype == B200PHY_F32
@@ -509,6 +515,11 @@ int b200phy_link_blast(int dtype, const b200phy_modem *modem, int Nr, int Nt, in
     if (filter_noise_var == 0.0 && Nt > Nr) { set_error("Blast ZF needs Nt <= Nr (got %dx%d)", Nr, Nt); return B200PHY_ERR_UNSUPPORTED; }
     if (S < 1) { set_error("S must be positive"); return B200PHY_ERR_INVALID; }
     if (!draws_consistent(idx, H, noise, true)) { set_error("stream mode needs idx, H, noise together"); return B200PHY_ERR_INVALID; }
+    {
+        const size_t ca = dtype == B200PHY_F32 ? 8 : 16;
+        if ((e = require_aligned(H, ca, "H")) || (e = require_aligned(noise, ca, "noise")) || (e = require_aligned(dec_out, ca, "dec_out")))
+            return e;
+    }
     if (n_units == 0) return B200PHY_OK;
     cudaStream_t st = (cudaStream_t)stream;
     return dtype == B200PHY_F32

@@ -75,6 +75,7 @@ static int fill_params(const b200phy_ofdm_tdl_params *q, const Modem &m, OfdmP *
     p.rx_scale = 1.0 / sqrt(power_scale);
     p.snt = sqrt(double(q->Nt));
     p.seed = q->seed;
+    p.rx_out = nullptr;
 
     // Jakes evaluation mode
     const double tol = q->dtype == B200PHY_F32 ? 2e-8 : 2e-14;
@@ -156,16 +157,24 @@ extern "C" {
 int b200phy_link_ofdm_tdl(const b200phy_ofdm_tdl_params *q, const b200phy_modem *modem,
                           uint64_t first_unit, int64_t n_units, const uint8_t *idx, const void *phi,
                           const void *psi, const void *noise, uint8_t *idx_hat, void *eq_out,
-                          int64_t *counters, void *stream) {
+                          void *rx_out, int64_t *counters, void *stream) {
     Modem m;
     int e = check_modem(modem, &m);
     if (e) return e;
     OfdmP p;
     if ((e = fill_params(q, m, &p))) return e;
+    p.rx_out = rx_out;
     if (!counters) { set_error("counters is NULL"); return B200PHY_ERR_INVALID; }
     if (n_units < 0) { set_error("n_units must be non-negative"); return B200PHY_ERR_INVALID; }
     const bool any = idx || phi || psi || noise, all = idx && phi && psi && noise;
     if (any && !all) { set_error("stream mode needs idx, phi, psi and noise together; fused mode needs all NULL"); return B200PHY_ERR_INVALID; }
+    {
+        const size_t rs = q->dtype == B200PHY_F32 ? 4 : 8;
+        if ((e = require_aligned(idx, 4, "idx")) || (e = require_aligned(phi, rs, "phi")) || (e = require_aligned(psi, rs, "psi")) ||
+            (e = require_aligned(noise, 2 * rs, "noise")) || (e = require_aligned(eq_out, 2 * rs, "eq_out")) ||
+            (e = require_aligned(rx_out, 2 * rs, "rx_out")))
+            return e;
+    }
     if (n_units == 0) return B200PHY_OK;
     cudaStream_t st = (cudaStream_t)stream;
     const int code = q->Nr * 10 + q->Nt;
@@ -181,6 +190,19 @@ int b200phy_link_ofdm_tdl(const b200phy_ofdm_tdl_params *q, const b200phy_modem 
             return B200PHY_ERR_UNSUPPORTED;
     }
 #undef B200_DISPATCH
+}
+
+int b200phy_ofdm_tdl_check_params(const b200phy_ofdm_tdl_params *q) {
+    OfdmP p;
+    Modem m = make_modem(B200PHY_MODEM_TABLE, 2);
+    int e = fill_params(q, m, &p);
+    if (e) return e;
+    switch (q->Nr * 10 + q->Nt) {
+        case 11: case 21: case 22: case 42: case 44: return B200PHY_OK;
+        default:
+            set_error("OFDM/TDL link is built for Nr x Nt in {1x1, 2x1, 2x2, 4x2, 4x4}; got %dx%d", q->Nr, q->Nt);
+            return B200PHY_ERR_UNSUPPORTED;
+    }
 }
 
 int b200phy_draw_ofdm_tdl(const b200phy_ofdm_tdl_params *q, int bits, uint64_t first_unit,

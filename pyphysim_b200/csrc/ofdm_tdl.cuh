@@ -55,6 +55,7 @@ struct OfdmP {
     double t0;
     double sigma, fnv, tx_scale, rx_scale, snt;
     uint64_t seed;
+    void *rx_out;   // optional: demodulated rx samples before detection, complex[n][Nr][n_sym*used] (parity tests)
 };
 
 template <typename T> struct OscRec { double th0, dl; cx<T> d; };
@@ -851,6 +852,11 @@ ofdm_tdl_kernel(const __grid_constant__ OfdmP p, const Modem m, const cx<T> *__r
                     cx<T> y[NR];
 #pragma unroll
                     for (int r = 0; r < NR; ++r) y[r] = rx_scale * Yp[r][k];
+                    if (p.rx_out) {
+#pragma unroll
+                        for (int r = 0; r < NR; ++r)
+                            static_cast<cx<T> *>(p.rx_out)[(size_t(frame) * NR + r) * (size_t(p.n_sym) * p.used) + size_t(s) * p.used + q] = y[r];
+                    }
                     cx<T> z[NT];
                     if constexpr (NR == 1 && NT == 1) {
                         z[0] = cdiv(y[0], H[u][0][0]);              // OfdmOneTapEqualizer (ofdm.py:510-511)

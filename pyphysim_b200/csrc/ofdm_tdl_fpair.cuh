@@ -3,7 +3,10 @@
 // FP32 instructions.  A pair sample is a float4 (A.re, B.re, A.im, B.im) for frames (A, B) = (2i, 2i+1):
 // the IFFT / FFT of both frames are one Stockham transform on float4 (ofdm_tdl_pair.cuh), the FIR multiplies
 // lane-wise (coefficient pairs x sample pairs), the one-tap equaliser runs per lane.  Semantics, draws and
-// error bounds are those of ofdm_tdl.cuh; an odd last frame is handled by the generic kernel.
+// error bounds are those of ofdm_tdl.cuh.  An odd last frame runs in lane 0 of a final pair whose lane 1 is a
+// masked copy of it (same reads, nothing counted or written): the two lanes are independent IEEE operations of
+// the same instruction stream, so a frame's result does not depend on its lane, its partner, the batch size or
+// the shard boundaries — counters stay a pure function of (seed, unit).
 #pragma once
 #include "ofdm_tdl_pair.cuh"
 
@@ -13,11 +16,12 @@ namespace b200phy {
 template <bool FUSED, bool QAMK, int LGF = 0>
 __global__ void __launch_bounds__(kOT, 3)
 ofdm_tdl_fpair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const cx<float> *__restrict__ tab_g,
-                      uint64_t first_unit, long long n_pairs, const uint8_t *__restrict__ idx_g,
+                      uint64_t first_unit, long long n_units, const uint8_t *__restrict__ idx_g,
                       const float *__restrict__ phi_g, const float *__restrict__ psi_g,
                       const cx<float> *__restrict__ noise_g, uint8_t *__restrict__ idx_hat,
                       cx<float> *__restrict__ eq_out, unsigned long long *counters) {
     using T = float;
+    const long long n_pairs = (n_units + 1) >> 1;
     Modem m = m_in;
     if (QAMK) m.kind = B200PHY_MODEM_QAM;      // compile-time kind (see ofdm_tdl_pair_kernel)
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -71,9 +75,11 @@ ofdm_tdl_fpair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const c
     const bool apipe = !FUSED;
     uint2 idx_pre = make_uint2(0u, 0u);
     auto prefetch = [&](long long f) {               // f = first frame of the pair
+        const bool ghost = f + 1 >= n_units;         // odd tail: lane 1 re-reads frame f
 #pragma unroll
         for (int ln = 0; ln < 2; ++ln) {
-            const T *gp = phi_g + size_t(f + ln) * p.P, *gq = psi_g + size_t(f + ln) * p.P;
+            const long long fl = (ln && !ghost) ? f + 1 : f;
+            const T *gp = phi_g + size_t(fl) * p.P, *gq = psi_g + size_t(fl) * p.P;
             T *dp = ph_phi + ln * p.P4, *dq = ph_psi + ln * p.P4;
             if (pf16) {
                 for (int i = tid; i < (p.P >> 2); i += kOT) {
@@ -87,7 +93,15 @@ ofdm_tdl_fpair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const c
                 }
             }
         }
-        if (tid < (p.n_data >> 2)) idx_pre = __ldg(reinterpret_cast<const uint2 *>(idx_g + size_t(f) * p.n_data) + tid);
+        if (tid < (p.n_data >> 2)) {
+            if (!ghost) {
+                idx_pre = __ldg(reinterpret_cast<const uint2 *>(idx_g + size_t(f) * p.n_data) + tid);
+            } else {
+                const uint32_t *w = reinterpret_cast<const uint32_t *>(idx_g + size_t(f) * p.n_data);
+                const int nw = p.n_data >> 2, w0 = 2 * tid, w1 = 2 * tid + 1;
+                idx_pre = make_uint2(__ldg(w + (w0 < nw ? w0 : w0 - nw)), __ldg(w + (w1 < nw ? w1 : w1 - nw)));
+            }
+        }
     };
     if constexpr (!FUSED) {
         if (pf && blockIdx.x < n_pairs) prefetch(2 * (long long)blockIdx.x);
@@ -95,14 +109,16 @@ ofdm_tdl_fpair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const c
     }
 
     for (long long pr = blockIdx.x; pr < n_pairs; pr += gridDim.x) {
-        const long long frame = 2 * pr;               // lane 0 = frame, lane 1 = frame + 1
+        const long long frame = 2 * pr;               // lane 0 = frame, lane 1 = frame + 1 (or a masked copy of frame)
+        const bool ghost = frame + 1 >= n_units;
+        const long long frameB = ghost ? frame : frame + 1;
         float4 *Y = pool, *W = pool + fft;
 
         // ---- phases of both frames -> shared memory
         if constexpr (FUSED) {
             for (int it = tid; it < 2 * (p.P4 >> 2); it += kOT) {
                 const int ln = it / (p.P4 >> 2), b = it - ln * (p.P4 >> 2);
-                const uint64_t unit = first_unit + uint64_t(frame + ln);
+                const uint64_t unit = first_unit + uint64_t(ln ? frameB : frame);
                 const uint4 b1 = rng_block(p.seed, STREAM_CHANNEL, unit, uint64_t(b));
                 const uint4 b2 = rng_block(p.seed, STREAM_CHANNEL, unit, uint64_t((p.P4 >> 2) + b));
 #pragma unroll
@@ -118,8 +134,8 @@ ofdm_tdl_fpair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const c
 #pragma unroll
             for (int ln = 0; ln < 2; ++ln)
                 for (int i = tid; i < p.P; i += kOT) {
-                    ph_phi[ln * p.P4 + i] = __ldg(phi_g + size_t(frame + ln) * p.P + i);
-                    ph_psi[ln * p.P4 + i] = __ldg(psi_g + size_t(frame + ln) * p.P + i);
+                    ph_phi[ln * p.P4 + i] = __ldg(phi_g + size_t(ln ? frameB : frame) * p.P + i);
+                    ph_psi[ln * p.P4 + i] = __ldg(psi_g + size_t(ln ? frameB : frame) * p.P + i);
                 }
         }
 
@@ -132,7 +148,7 @@ ofdm_tdl_fpair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const c
                     const int b0 = w0 >> 2, nb = ((w0 + cnt - 1) >> 2) - b0 + 1;
                     for (int it = tid; it < 2 * nb; it += kOT) {
                         const int ln = it / nb, b = b0 + it - ln * nb;
-                        const uint4 blk = rng_block(p.seed, STREAM_DATA, first_unit + uint64_t(frame + ln), uint64_t(b));
+                        const uint4 blk = rng_block(p.seed, STREAM_DATA, first_unit + uint64_t(ln ? frameB : frame), uint64_t(b));
 #pragma unroll
                         for (int l = 0; l < 4; ++l) {
                             const int w = 4 * b + l - w0;
@@ -142,7 +158,7 @@ ofdm_tdl_fpair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const c
                 } else if (!pf) {
 #pragma unroll
                     for (int ln = 0; ln < 2; ++ln) {
-                        const uint8_t *src = idx_g + size_t(frame + ln) * p.n_data + w0;
+                        const uint8_t *src = idx_g + size_t(ln ? frameB : frame) * p.n_data + w0;
                         for (int i = tid; i < cnt; i += kOT) dsym[ln * used + i] = src[i];
                     }
                 }
@@ -151,7 +167,7 @@ ofdm_tdl_fpair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const c
                     const int pr0 = m0 >> 1, npr = ((m0 + fft - 1) >> 1) - pr0 + 1;
                     for (int it = tid; it < 2 * npr; it += kOT) {
                         const int ln = it / npr, q = pr0 + it - ln * npr;
-                        const uint4 blk = rng_block(p.seed, STREAM_NOISE, first_unit + uint64_t(frame + ln), uint64_t(q));
+                        const uint4 blk = rng_block(p.seed, STREAM_NOISE, first_unit + uint64_t(ln ? frameB : frame), uint64_t(q));
                         const int j = 2 * q - m0;
                         float *yr = reinterpret_cast<float *>(Y) + ln;
                         if (j >= 0 && j < fft) { const cx<T> c = sigma * cnormal<T>(blk.x, blk.y); yr[4 * j] = c.re; yr[4 * j + 2] = c.im; }
@@ -159,7 +175,7 @@ ofdm_tdl_fpair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const c
                     }
                 } else if (apipe) {
                     const size_t rowlen = size_t(p.N + mem);
-                    const cx<T> *s0 = noise_g + size_t(frame) * rowlen + m0, *s1 = s0 + rowlen;
+                    const cx<T> *s0 = noise_g + size_t(frame) * rowlen + m0, *s1 = noise_g + size_t(frameB) * rowlen + m0;
                     // sample j of frame A / frame B lands in the two halves of float4 slot j (see ofdm_tdl_pair.cuh):
                     // in-place pair relayout in the FIR epilogue, each thread consumes only its own copies
                     cx<T> *raw = reinterpret_cast<cx<T> *>(Y);
@@ -170,7 +186,7 @@ ofdm_tdl_fpair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const c
                     cp_async_commit();
                 } else {
                     const size_t rowlen = size_t(p.N + mem);
-                    const cx<T> *s0 = noise_g + size_t(frame) * rowlen + m0, *s1 = s0 + rowlen;
+                    const cx<T> *s0 = noise_g + size_t(frame) * rowlen + m0, *s1 = noise_g + size_t(frameB) * rowlen + m0;
                     for (int j0 = tid; j0 < fft; j0 += 4 * kOT) {
                         cx<T> v0[4], v1[4];
 #pragma unroll
@@ -401,6 +417,7 @@ ofdm_tdl_fpair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const c
                     upk2(Hk[u].im, hi0, hi1);
 #pragma unroll
                     for (int ln = 0; ln < 2; ++ln) {
+                        if (ln && ghost) continue;
                         const cx<T> y = ln ? mk<T>(rx_scale * yr1, rx_scale * yi1) : mk<T>(rx_scale * yr0, rx_scale * yi0);
                         const cx<T> H = ln ? mk<T>(hr1, hi1) : mk<T>(hr0, hi0);
                         const cx<T> z = cdiv(y, H);
@@ -411,6 +428,7 @@ ofdm_tdl_fpair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const c
                         const size_t o = size_t(frame + ln) * p.n_data + size_t(s * used + q);
                         if (idx_hat) idx_hat[o] = uint8_t(e);
                         if (eq_out) eq_out[o] = z;
+                        if (p.rx_out) static_cast<cx<T> *>(p.rx_out)[o] = y;
                     }
                 }
             }
@@ -419,8 +437,8 @@ ofdm_tdl_fpair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const c
     }       // frame pairs
     flush_counters(sym_err, bit_err, counters);
     if (blockIdx.x == 0 && tid == 0) {
-        atomicAdd(&counters[2], (unsigned long long)n_pairs * 2 * p.n_data);
-        atomicAdd(&counters[3], (unsigned long long)n_pairs * 2 * p.n_data * m.bits);
+        atomicAdd(&counters[2], (unsigned long long)n_units * p.n_data);
+        atomicAdd(&counters[3], (unsigned long long)n_units * p.n_data * m.bits);
     }
 }
 

@@ -108,7 +108,7 @@ static int launch_pair(const OfdmP &p, const Modem &m, const void *table, uint64
 }
 
 template <bool FUSED, bool QAMK, int LGF>
-static int launch_fpair_kl(const OfdmP &p, const Modem &m, const void *table, uint64_t first_unit, int64_t n_pairs,
+static int launch_fpair_kl(const OfdmP &p, const Modem &m, const void *table, uint64_t first_unit, int64_t n_units,
                         const uint8_t *idx, const void *phi, const void *psi, const void *noise,
                         uint8_t *idx_hat, void *eq_out, int64_t *counters, size_t smem, cudaStream_t st) {
     auto kern = ofdm_tdl_fpair_kernel<FUSED, QAMK, LGF>;
@@ -122,9 +122,10 @@ static int launch_fpair_kl(const OfdmP &p, const Modem &m, const void *table, ui
                    "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
     if (e) return e;
     if (occ < 1) return -1;
+    const int64_t n_pairs = (n_units + 1) / 2;
     long long grid = (long long)sms * occ;
     if (grid > n_pairs) grid = n_pairs;
-    kern<<<int(grid), kOT, smem, st>>>(p, m, (const cx<float> *)table, first_unit, (long long)n_pairs, idx,
+    kern<<<int(grid), kOT, smem, st>>>(p, m, (const cx<float> *)table, first_unit, (long long)n_units, idx,
                                        (const float *)phi, (const float *)psi, (const cx<float> *)noise,
                                        idx_hat, (cx<float> *)eq_out, (unsigned long long *)counters);
     count_launch();
@@ -132,23 +133,23 @@ static int launch_fpair_kl(const OfdmP &p, const Modem &m, const void *table, ui
 }
 
 template <bool FUSED, bool QAMK>
-static int launch_fpair_k(const OfdmP &p, const Modem &m, const void *table, uint64_t first_unit, int64_t n_pairs,
+static int launch_fpair_k(const OfdmP &p, const Modem &m, const void *table, uint64_t first_unit, int64_t n_units,
                         const uint8_t *idx, const void *phi, const void *psi, const void *noise,
                         uint8_t *idx_hat, void *eq_out, int64_t *counters, size_t smem, cudaStream_t st) {
 #if B200_PAIR_STATIC_SHAPE
     if (p.fft == 1024 && p.used == p.fft)
-        return launch_fpair_kl<FUSED, QAMK, 10>(p, m, table, first_unit, n_pairs, idx, phi, psi, noise, idx_hat, eq_out, counters, smem, st);
+        return launch_fpair_kl<FUSED, QAMK, 10>(p, m, table, first_unit, n_units, idx, phi, psi, noise, idx_hat, eq_out, counters, smem, st);
 #endif
-    return launch_fpair_kl<FUSED, QAMK, 0>(p, m, table, first_unit, n_pairs, idx, phi, psi, noise, idx_hat, eq_out, counters, smem, st);
+    return launch_fpair_kl<FUSED, QAMK, 0>(p, m, table, first_unit, n_units, idx, phi, psi, noise, idx_hat, eq_out, counters, smem, st);
 }
 
 template <bool FUSED>
-static int launch_fpair(const OfdmP &p, const Modem &m, const void *table, uint64_t first_unit, int64_t n_pairs,
+static int launch_fpair(const OfdmP &p, const Modem &m, const void *table, uint64_t first_unit, int64_t n_units,
                         const uint8_t *idx, const void *phi, const void *psi, const void *noise,
                         uint8_t *idx_hat, void *eq_out, int64_t *counters, size_t smem, cudaStream_t st) {
     if (m.kind == B200PHY_MODEM_QAM)
-        return launch_fpair_k<FUSED, true>(p, m, table, first_unit, n_pairs, idx, phi, psi, noise, idx_hat, eq_out, counters, smem, st);
-    return launch_fpair_k<FUSED, false>(p, m, table, first_unit, n_pairs, idx, phi, psi, noise, idx_hat, eq_out, counters, smem, st);
+        return launch_fpair_k<FUSED, true>(p, m, table, first_unit, n_units, idx, phi, psi, noise, idx_hat, eq_out, counters, smem, st);
+    return launch_fpair_k<FUSED, false>(p, m, table, first_unit, n_units, idx, phi, psi, noise, idx_hat, eq_out, counters, smem, st);
 }
 
 template <typename T, int NR, int NT>
@@ -160,28 +161,14 @@ static int launch_typed(const OfdmP &p, const Modem &m, const void *table, uint6
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     if constexpr (std::is_same<T, float>::value && NR == 1 && NT == 1) {
-        // SISO: two frames per CTA on the two lanes of the packed FP32 pipe; an odd last frame goes generic
-        if (ofdm_tdl_fpair_ok(p) && n_units >= 2) {
+        // SISO: two frames per CTA on the two lanes of the packed FP32 pipe (an odd last frame runs in a
+        // final pair with a masked second lane, so every frame takes the same arithmetic whatever the batch)
+        if (ofdm_tdl_fpair_ok(p)) {
             const size_t fs = ofdm_tdl_fpair_smem(p, m.M);
             if (fs <= size_t(max_smem)) {
-                const int64_t n_pairs = n_units / 2;
-                const int e = idx ? launch_fpair<false>(p, m, table, first_unit, n_pairs, idx, phi, psi, noise, idx_hat, eq_out, counters, fs, st)
-                                  : launch_fpair<true>(p, m, table, first_unit, n_pairs, idx, phi, psi, noise, idx_hat, eq_out, counters, fs, st);
-                if (e > 0) return e;
-                if (e == 0) {
-                    const int64_t done = 2 * n_pairs;
-                    if (done == n_units) return 0;
-                    first_unit += uint64_t(done);
-                    n_units -= done;
-                    if (idx) {
-                        idx += size_t(done) * p.n_data;
-                        phi = (const float *)phi + size_t(done) * p.P;
-                        psi = (const float *)psi + size_t(done) * p.P;
-                        noise = (const cx<float> *)noise + size_t(done) * size_t(p.N + p.mem);
-                    }
-                    if (idx_hat) idx_hat += size_t(done) * p.n_data;
-                    if (eq_out) eq_out = (cx<float> *)eq_out + size_t(done) * p.n_data;
-                }
+                const int e = idx ? launch_fpair<false>(p, m, table, first_unit, n_units, idx, phi, psi, noise, idx_hat, eq_out, counters, fs, st)
+                                  : launch_fpair<true>(p, m, table, first_unit, n_units, idx, phi, psi, noise, idx_hat, eq_out, counters, fs, st);
+                if (e >= 0) return e;
             }
         }
     }

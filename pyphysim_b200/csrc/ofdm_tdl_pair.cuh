@@ -816,6 +816,18 @@ ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const cx
 #pragma unroll
                         for (int t = 0; t < NT; ++t) eq_fs[q * NT + t] = z[u][t];
                     }
+                    if (p.rx_out) {
+                        // slow path (parity tests): the demodulated rx samples of this bin, re-derived from the packed bins
+#pragma unroll
+                        for (int qq = 0; qq < NP; ++qq) {
+                            float yr0, yr1, yi0, yi1;
+                            upk2(Yv[qq][u].re, yr0, yr1);
+                            upk2(Yv[qq][u].im, yi0, yi1);
+                            cx<T> *ro = static_cast<cx<T> *>(p.rx_out) + (size_t(frame) * NR + 2 * qq) * (size_t(p.n_sym) * used) + size_t(s) * used + q;
+                            ro[0] = {rx_scale * yr0, rx_scale * yi0};
+                            ro[size_t(p.n_sym) * used] = {rx_scale * yr1, rx_scale * yi1};
+                        }
+                    }
                 }
             }
             __syncthreads();

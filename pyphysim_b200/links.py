@@ -15,6 +15,9 @@ import numpy as np
 from . import SEED_DEFAULT, _lib
 
 
+MIMO_SCHEMES = {'svd': 1, 'gmd': 2, 'mrt': 3}
+
+
 def _modem(modulator, dtype):
     return modulator._native(dtype)
 
@@ -70,6 +73,15 @@ class OfdmTdlLink:
         self.P = L * tap_delays.size * Nr * Nt
         self.Nr, self.Nt = Nr, Nt
 
+    def with_dtype(self, dtype):
+        """The same link in another arithmetic ('f32' / 'f64'): same parameters, seed and draws layout."""
+        import copy
+        other = copy.copy(self)
+        other.params = _lib.OfdmTdlParams.from_buffer_copy(self.params)
+        other.dtype = _lib.parse_dtype(dtype)
+        other.params.dtype = other.dtype
+        return other
+
     def set_noise_var(self, noise_var, filter_noise_var=None):
         self.params.noise_var = float(noise_var)
         self.params.filter_noise_var = float(noise_var if filter_noise_var is None else filter_noise_var)
@@ -95,9 +107,11 @@ class OfdmTdlLink:
                                              _lib.ptr(noise), _lib.cur_stream()))
         return idx, phi, psi, noise
 
-    def run(self, n_units, first_unit=0, draws=None, counters=None, want_idx=False, want_eq=False):
+    def run(self, n_units, first_unit=0, draws=None, counters=None, want_idx=False, want_eq=False,
+            want_rx=False):
         """Simulate frames [first_unit, first_unit + n_units).  Returns counters (NumPy int64[4], or
-        the device tensor passed in — then nothing synchronises) [, idx_hat][, equalised symbols]."""
+        the device tensor passed in — then nothing synchronises) [, idx_hat][, equalised symbols]
+        [, demodulated rx samples before detection: complex[n, Nr, n_sym*used]]."""
         lib = _lib.load()
         torch = _lib.torch_cuda()
         modem, keep = _modem(self.modulator, self.dtype)
@@ -108,11 +122,13 @@ class OfdmTdlLink:
         hat = torch.empty((n_units, self.n_data), dtype=torch.uint8, device='cuda') if want_idx else None
         eq = torch.empty((n_units, self.n_data), dtype=_lib.cplx_dtype(self.dtype), device='cuda') \
             if want_eq else None
+        rx = torch.empty((n_units, self.Nr, self.n_data // self.Nt), dtype=_lib.cplx_dtype(self.dtype),
+                         device='cuda') if want_rx else None
         _lib.check(lib.b200phy_link_ofdm_tdl(C.byref(self.params), modem, first_unit, n_units,
                                              _lib.ptr(idx), _lib.ptr(phi), _lib.ptr(psi),
-                                             _lib.ptr(noise), _lib.ptr(hat), _lib.ptr(eq),
+                                             _lib.ptr(noise), _lib.ptr(hat), _lib.ptr(eq), _lib.ptr(rx),
                                              _lib.ptr(cnt), _lib.cur_stream()))
-        return _finish(cnt, own, [hat, eq])
+        return _finish(cnt, own, [hat, eq, rx])
 
     def run_host(self, n_units, first_unit=0, draws=None, want_idx=False):
         """Same through the host-buffer C entry point (``b200phy_link_ofdm_tdl_host``): draws are
@@ -174,6 +190,70 @@ def link_siso_flat_host(modulator, noise_var, n_units, *, rayleigh=True, seed=SE
     return (cnt, hat) if want_idx else cnt
 
 
+def _host_table(modulator):
+    table = np.ascontiguousarray(np.asarray(modulator.symbols, dtype=np.complex128))
+    return table, table.view(np.float64).ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _host_out(n_units, per_unit, want_idx):
+    if not want_idx:
+        return None
+    import torch
+    return torch.empty((n_units, per_unit), dtype=torch.uint8, pin_memory=True)
+
+
+def link_alamouti_host(modulator, noise_var, n_units, *, Nr=2, num_symbols=2, seed=SEED_DEFAULT,
+                       first_unit=0, dtype='f32', draws=None, want_idx=False):
+    """`link_alamouti` through the host-buffer C entry point (``b200phy_link_alamouti_host``): draws
+    are host tensors (or None = Monte Carlo mode: parameters in, 32 bytes of counters out)."""
+    lib = _lib.load()
+    dt = _lib.parse_dtype(dtype)
+    table, tp = _host_table(modulator)
+    cnt = np.zeros(4, dtype=np.int64)
+    idx, H, noise = draws if draws is not None else (None, None, None)
+    hat = _host_out(n_units, num_symbols, want_idx)
+    _lib.check(lib.b200phy_link_alamouti_host(dt, modulator._kind, modulator.M, tp, Nr, num_symbols,
+                                              float(noise_var), seed, first_unit, n_units, _lib.ptr(idx),
+                                              _lib.ptr(H), _lib.ptr(noise), _lib.ptr(hat),
+                                              cnt.ctypes.data_as(C.POINTER(C.c_int64))))
+    return (cnt, hat) if want_idx else cnt
+
+
+def link_blast_host(modulator, noise_var, n_units, *, Nr=2, Nt=2, num_symbols=1, filter_noise_var=0.0,
+                    seed=SEED_DEFAULT, first_unit=0, dtype='f32', draws=None, want_idx=False):
+    """`link_blast` through ``b200phy_link_blast_host`` (host draws or Monte Carlo mode)."""
+    lib = _lib.load()
+    dt = _lib.parse_dtype(dtype)
+    table, tp = _host_table(modulator)
+    cnt = np.zeros(4, dtype=np.int64)
+    idx, H, noise = draws if draws is not None else (None, None, None)
+    hat = _host_out(n_units, num_symbols * Nt, want_idx)
+    _lib.check(lib.b200phy_link_blast_host(dt, modulator._kind, modulator.M, tp, Nr, Nt, num_symbols,
+                                           float(noise_var), float(filter_noise_var), seed, first_unit, n_units,
+                                           _lib.ptr(idx), _lib.ptr(H), _lib.ptr(noise), _lib.ptr(hat),
+                                           cnt.ctypes.data_as(C.POINTER(C.c_int64))))
+    return (cnt, hat) if want_idx else cnt
+
+
+def link_precoded_host(modulator, noise_var, n_units, *, scheme, Nr, Nt, num_symbols=1, filter_noise_var=0.0,
+                       seed=SEED_DEFAULT, first_unit=0, dtype='f32', draws=None, want_idx=False):
+    """`link_precoded` through ``b200phy_link_precoded_host`` (host draws or Monte Carlo mode)."""
+    lib = _lib.load()
+    dt = _lib.parse_dtype(dtype)
+    if scheme not in MIMO_SCHEMES:
+        raise ValueError("scheme must be one of %s" % sorted(MIMO_SCHEMES))
+    table, tp = _host_table(modulator)
+    cnt = np.zeros(4, dtype=np.int64)
+    idx, H, noise = draws if draws is not None else (None, None, None)
+    layers = 1 if scheme == 'mrt' else Nt
+    hat = _host_out(n_units, num_symbols * layers, want_idx)
+    _lib.check(lib.b200phy_link_precoded_host(dt, modulator._kind, modulator.M, tp, MIMO_SCHEMES[scheme], Nr, Nt,
+                                              num_symbols, float(noise_var), float(filter_noise_var), seed,
+                                              first_unit, n_units, _lib.ptr(idx), _lib.ptr(H), _lib.ptr(noise),
+                                              _lib.ptr(hat), cnt.ctypes.data_as(C.POINTER(C.c_int64))))
+    return (cnt, hat) if want_idx else cnt
+
+
 def draw_siso_flat(modulator, n_units, *, rayleigh=True, seed=SEED_DEFAULT, first_unit=0, dtype='f32'):
     lib = _lib.load()
     torch = _lib.torch_cuda()
@@ -229,9 +309,6 @@ def link_blast(modulator, noise_var, n_units, *, Nr=2, Nt=2, num_symbols=1, filt
                                       _lib.ptr(noise), _lib.ptr(hat), _lib.ptr(dec), _lib.ptr(cnt),
                                       _lib.cur_stream()))
     return _finish(cnt, own, [hat, dec])
-
-
-MIMO_SCHEMES = {'svd': 1, 'gmd': 2, 'mrt': 3}
 
 
 def link_precoded(modulator, noise_var, n_units, *, scheme, Nr, Nt, num_symbols=1, filter_noise_var=0.0,

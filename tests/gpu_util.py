@@ -30,16 +30,38 @@ def cuda(a, dtype=None):
     return t.cuda()
 
 
-def assert_samples_close(dev, ref, rel=1e-5, what=''):
+def assert_samples_close(dev, ref, rel=1e-5, what='', tol=None):
     """|dev - ref| <= rel * max(|ref|, rms(ref)) (SURVEY.md §7 hard part 2: pointwise relative error
-    is meaningless in deep fades, so the floor is the rms)."""
+    is meaningless in deep fades, so the floor is the rms).  `tol`: explicit per-sample bound instead.
+    Returns the worst err / tol ratio."""
     dev = np.asarray(dev).astype(np.complex128).reshape(-1)
     ref = np.asarray(ref).astype(np.complex128).reshape(-1)
-    rms = np.sqrt(np.mean(np.abs(ref) ** 2))
-    tol = rel * np.maximum(np.abs(ref), rms)
+    if tol is None:
+        rms = np.sqrt(np.mean(np.abs(ref) ** 2))
+        tol = rel * np.maximum(np.abs(ref), rms)
+    tol = np.asarray(tol, dtype=np.float64).reshape(-1)
     err = np.abs(dev - ref)
     worst = np.argmax(err / tol)
     assert np.all(err <= tol), '%s: worst err %.3g vs tol %.3g at %d' % (what, err[worst], tol[worst], worst)
+    return float(err[worst] / tol[worst])
+
+
+def mimo_eq_tolerance(det, rel, Nr, Nt):
+    """Per-symbol error bound of the detected symbols z_k = G_k y_k when the demodulated rx samples y_k and
+    the channel H_k each carry a relative error `rel` (first order):
+        |dz| <= ||G_k||_2 * rel * ( max(||y_k||_2, rms ||y||_2) + ||H_k||_F * ||z_k||_2 )
+    (dz = G dy + dG y with dG = -G dH G, so dG y = -G dH z).  det: `detail` of oracle.links.ofdm_tdl_frame.
+    Returns tol[n_sym*used*Nt] in the layout of the equalised symbols (symbol j*Nt + t)."""
+    G, Hk = det['G'], det['Hk']                         # [K, Nt, Nr], [K, Nr, Nt]
+    K = G.shape[0]
+    y = np.moveaxis(det['Y'].reshape(Nr, K), 0, -1)    # [K, Nr]
+    z = det['eq'].reshape(K, Nt)
+    gn = np.linalg.norm(G, 2, axis=(1, 2))
+    yn = np.linalg.norm(y, axis=1)
+    yn = np.maximum(yn, np.sqrt(np.mean(yn ** 2)))
+    hn = np.linalg.norm(Hk, 'fro', axis=(1, 2))
+    zn = np.linalg.norm(z, axis=1)
+    return np.repeat(rel * gn * (yn + hn * zn), Nt)
 
 
 def decision_margin(modem, r):
@@ -53,7 +75,9 @@ def decision_margin(modem, r):
 
 def assert_decisions(dev_idx, ref_idx, modem, ref_samples, exact, eps=2e-4, what=''):
     """exact: indices identical.  Otherwise (float32 arithmetic vs the float64 oracle) any mismatch
-    must sit on a decision boundary: oracle margin below eps, and be rare."""
+    must sit on a decision boundary: oracle margin (distance gap between the two nearest constellation
+    points, which a sample error e can close only if it is < 2 e) below eps — a scalar or one value per
+    symbol — and be rare."""
     dev_idx = np.asarray(dev_idx).reshape(-1).astype(np.int64)
     ref_idx = np.asarray(ref_idx).reshape(-1).astype(np.int64)
     bad = np.nonzero(dev_idx != ref_idx)[0]
@@ -62,7 +86,9 @@ def assert_decisions(dev_idx, ref_idx, modem, ref_samples, exact, eps=2e-4, what
         return 0
     if bad.size:
         marg = decision_margin(modem, np.asarray(ref_samples).reshape(-1)[bad])
-        assert np.all(marg < eps), '%s: mismatch with margin %.3g' % (what, marg.max())
+        lim = eps if np.isscalar(eps) else np.asarray(eps).reshape(-1)[bad]
+        assert np.all(marg < lim), '%s: mismatch with margin %.3g (limit %.3g)' % (
+            what, marg.max(), np.max(lim))
         assert bad.size <= max(2, 1e-3 * dev_idx.size), '%s: %d mismatches' % (what, bad.size)
     return bad.size
 

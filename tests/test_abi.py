@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), n
     assert sorted(_lib.SIGNATURES) == names          # binding covers the whole header, nothing else
-    assert lib.b200phy_version() == 100
+    assert lib.b200phy_version() == 101
     assert lib.b200phy_launch_count() == 0           # no compute without a GPU
 
 
@@ -98,10 +98,36 @@ def test_argument_validation_needs_no_gpu():
     p.struct_size = C.sizeof(p)
     p.fft, p.cp, p.used, p.n_sym, p.Nr, p.Nt, p.n_taps, p.L = 64, 65, 52, 1, 1, 1, 1, 8
     p.Ts, p.tap_powers[0] = 1e-6, 1.0
-    rc = lib.b200phy_link_ofdm_tdl(C.byref(p), m, 0, 1, None, None, None, None, None, None,
+    rc = lib.b200phy_link_ofdm_tdl(C.byref(p), m, 0, 1, None, None, None, None, None, None, None,
                                    C.cast(cnt, C.c_void_p), None)
     assert rc == _lib.ERR_INVALID and b'cp_size' in lib.b200phy_last_error()
     p.cp, p.used = 16, 51
-    rc = lib.b200phy_link_ofdm_tdl(C.byref(p), m, 0, 1, None, None, None, None, None, None,
+    rc = lib.b200phy_link_ofdm_tdl(C.byref(p), m, 0, 1, None, None, None, None, None, None, None,
                                    C.cast(cnt, C.c_void_p), None)
     assert rc == _lib.ERR_INVALID and b'multiple of 2' in lib.b200phy_last_error()
+    # the parameter check alone (what the host-buffer entry points run before they size any copy)
+    assert lib.b200phy_ofdm_tdl_check_params(C.byref(p)) == _lib.ERR_INVALID
+    p.used = 52
+    assert lib.b200phy_ofdm_tdl_check_params(C.byref(p)) == 0
+    p.struct_size = 8
+    assert lib.b200phy_ofdm_tdl_check_params(C.byref(p)) == _lib.ERR_INVALID and b'size mismatch' in lib.b200phy_last_error()
+    p.struct_size = C.sizeof(p)
+    p.Nr, p.Nt = 3, 2
+    assert lib.b200phy_ofdm_tdl_check_params(C.byref(p)) == _lib.ERR_UNSUPPORTED
+    # host entry points validate before touching the device: bad arguments fail here even without a GPU
+    cnt64 = (C.c_int64 * 4)()
+    p.Nr, p.Nt, p.n_taps = 1, 1, 99
+    rc = lib.b200phy_link_ofdm_tdl_host(C.byref(p), _lib.MODEM_QAM, 16, None, 0, 4, None, None, None, None, None, cnt64)
+    assert rc in (_lib.ERR_INVALID, _lib.ERR_UNSUPPORTED) and b'n_taps' in lib.b200phy_last_error()
+    tab = (C.c_double * 8)()
+    rc = lib.b200phy_link_alamouti_host(_lib.F32, _lib.MODEM_QPSK, 4, tab, 2, 3, 0.1, 1, 0, 8, None, None, None, None, cnt64)
+    assert rc == _lib.ERR_INVALID and b'even' in lib.b200phy_last_error()
+    one = (C.c_uint8 * 8)()
+    rc = lib.b200phy_link_blast_host(_lib.F32, _lib.MODEM_QPSK, 4, tab, 2, 2, 1, 0.1, 0.0, 1, 0, 8,
+                                     C.cast(one, C.c_void_p), None, None, None, cnt64)
+    assert rc == _lib.ERR_INVALID and b'together' in lib.b200phy_last_error()
+    rc = lib.b200phy_link_precoded_host(_lib.F32, _lib.MODEM_QPSK, 4, tab, 9, 2, 2, 1, 0.1, 0.0, 1, 0, 8, None, None,
+                                        None, None, cnt64)
+    assert rc == _lib.ERR_INVALID and b'scheme' in lib.b200phy_last_error()
+    rc = lib.b200phy_link_siso_flat_host(_lib.F32, _lib.MODEM_QAM, 16, None, 1, 0.1, 1, 0, 8, None, None, None, None, cnt64)
+    assert rc == _lib.ERR_INVALID and b'table_re_im' in lib.b200phy_last_error()
