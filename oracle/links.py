@@ -191,6 +191,9 @@ def ofdm_tdl_frame(cfg, idx, phi, psi, noise, reference_equalizer=False, detail=
         if cfg.mimo and not per_subcarrier_loop:
             det['G'] = G                                                     # [n_sym*used, Nt, Nr]
             det['Hk'] = Hk.reshape(-1, cfg.Nr, cfg.Nt)
+        elif not cfg.mimo:
+            Hk = Hm[:, ofdm.used_subcarrier_indexes(cfg.fft, cfg.used)].reshape(-1, 1, 1)
+            det['G'], det['Hk'] = 1.0 / Hk, Hk                               # the one-tap "filter"
         return idx_hat, det
     return idx_hat
 

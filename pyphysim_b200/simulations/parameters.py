@@ -144,16 +144,19 @@ class SimulationParameters:
             return pickle.load(fh)
 
     def to_dict(self):
+        """The JSON schema of the reference (parameters.py:`_to_dict` + util/serialize.py:36-66): arrays as
+        {data, dtype, _is_numpy_array, shape}, sets as {data, _is_set} — files stay readable by its
+        `SimulationResults.load_from_file`."""
         def conv(v):
             if isinstance(v, np.ndarray):
-                return {'__ndarray__': v.tolist(), 'dtype': str(v.dtype)}
+                return {'data': v.tolist(), 'dtype': str(v.dtype), '_is_numpy_array': True, 'shape': list(v.shape)}
             if isinstance(v, (np.integer,)):
                 return int(v)
             if isinstance(v, (np.floating,)):
                 return float(v)
             return v
         return {'parameters': {k: conv(v) for k, v in self.parameters.items()},
-                'unpacked_parameters_set': sorted(self._unpacked_parameters_set),
+                'unpacked_parameters_set': {'data': sorted(self._unpacked_parameters_set), '_is_set': True},
                 'unpack_index': self._unpack_index,
                 'original_sim_params': None if self._original_sim_params is None
                 else self._original_sim_params.to_dict()}
@@ -161,14 +164,18 @@ class SimulationParameters:
     @staticmethod
     def from_dict(d):
         def conv(v):
-            if isinstance(v, dict) and '__ndarray__' in v:
+            if isinstance(v, dict) and v.get('_is_numpy_array') is True:
+                return np.array(v['data'])               # like json_numpy_or_set_obj_hook (serialize.py:87-91)
+            if isinstance(v, dict) and v.get('_is_set') is True:
+                return set(v['data'])
+            if isinstance(v, dict) and '__ndarray__' in v:      # files written by pyphysim_b200 0.1.0
                 return np.array(v['__ndarray__'], dtype=v['dtype'])
             return v
         sp = SimulationParameters()
         if not d:
             return sp
         sp.parameters = {k: conv(v) for k, v in d['parameters'].items()}
-        sp._unpacked_parameters_set = set(d['unpacked_parameters_set'])
+        sp._unpacked_parameters_set = set(conv(d['unpacked_parameters_set']))
         sp._unpack_index = d['unpack_index']
         if d.get('original_sim_params') is not None:
             sp._original_sim_params = SimulationParameters.from_dict(d['original_sim_params'])

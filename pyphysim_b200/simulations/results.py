@@ -22,6 +22,36 @@ def calc_confidence_interval(mean, std, n, P=95.0):
     return mean - half, mean + half
 
 
+_OWN, _REF = 'pyphysim_b200.simulations', 'pyphysim.simulations'
+
+
+class _ReferencePathPickler(pickle._Pickler):
+    """Pickle files carry class paths.  The reference writes `pyphysim.simulations.results.SimulationResults`
+    (results.py:1454-1473, protocol 2); so does this pickler for the classes of this package, which keeps
+    result files — final and partial — loadable by the reference's own `load_from_file` and
+    `bin/combine_results.py`.  Pure-Python pickler: result files are a few KB."""
+
+    def save_global(self, obj, name=None):
+        mod = getattr(obj, '__module__', None) or ''
+        if mod == _OWN or mod.startswith(_OWN + '.'):
+            qual = getattr(obj, '__qualname__', None) or obj.__name__
+            self.write(pickle.GLOBAL + (_REF + mod[len(_OWN):]).encode('utf-8') + b'\n' +
+                       qual.encode('utf-8') + b'\n')
+            self.memoize(obj)
+            return
+        super().save_global(obj, name)
+
+
+class _ReferencePathUnpickler(pickle.Unpickler):
+    """...and files written by the reference (or by the pickler above) resolve to this package's classes,
+    whether or not the `pyphysim` alias package is importable."""
+
+    def find_class(self, module, name):
+        if module == _REF or module.startswith(_REF + '.'):
+            module = _OWN + module[len(_REF):]
+        return super().find_class(module, name)
+
+
 class Result:
     """One named statistic with an update rule (results.py:128-786)."""
 
@@ -352,7 +382,7 @@ class SimulationResults:
                 fh.write(self.to_json())
         elif ext == '.pickle':
             with open(filename, 'wb') as fh:
-                pickle.dump(self, fh, protocol=2)
+                _ReferencePathPickler(fh, protocol=2).dump(self)
         else:
             raise KeyError(ext)
         return filename
@@ -366,7 +396,7 @@ class SimulationResults:
             with open(filename, 'r') as fh:
                 return SimulationResults.from_json(fh.read())
         with open(filename, 'rb') as fh:
-            obj = pickle.load(fh)
+            obj = _ReferencePathUnpickler(fh).load()
         assert isinstance(obj, SimulationResults)
         return obj
 

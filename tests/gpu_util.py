@@ -46,9 +46,9 @@ def assert_samples_close(dev, ref, rel=1e-5, what='', tol=None):
     return float(err[worst] / tol[worst])
 
 
-def mimo_eq_tolerance(det, rel, Nr, Nt):
-    """Per-symbol error bound of the detected symbols z_k = G_k y_k when the demodulated rx samples y_k and
-    the channel H_k each carry a relative error `rel` (first order):
+def eq_tolerance(det, rel, Nr, Nt):
+    """Per-symbol error bound of the detected symbols z_k = G_k y_k (SISO: G_k = 1 / H_k, the one-tap equaliser)
+    when the demodulated rx samples y_k and the channel H_k each carry a relative error `rel` (first order):
         |dz| <= ||G_k||_2 * rel * ( max(||y_k||_2, rms ||y||_2) + ||H_k||_F * ||z_k||_2 )
     (dz = G dy + dG y with dG = -G dH G, so dG y = -G dH z).  det: `detail` of oracle.links.ofdm_tdl_frame.
     Returns tol[n_sym*used*Nt] in the layout of the equalised symbols (symbol j*Nt + t)."""

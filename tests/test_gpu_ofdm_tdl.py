@@ -7,7 +7,7 @@ from oracle import fading
 from oracle import links as OL
 from oracle import modulators as md
 
-from gpu_util import (assert_decisions, assert_samples_close, cuda, mimo_eq_tolerance, oracle_modem, product_modem)
+from gpu_util import (assert_decisions, assert_samples_close, cuda, eq_tolerance, oracle_modem, product_modem)
 
 pytestmark = pytest.mark.gpu
 SEED = 0xC0FFEE
@@ -33,17 +33,19 @@ def make_pair(kind, M, fft, cp, used, n_sym=1, Nr=1, Nt=1, profile=fading.COST25
 
 
 REL_F32 = 1e-5      # BASELINE.json north_star: complex sample values within 1e-5 relative
+DEC_REL = 2e-6      # decisions: a mismatch must sit within 4x the bound at this (measured-error-sized) level
 
 
 def run_stream_vs_oracle(cfg, link, units, exact, rel, eps=2e-4):
     """Host Philox draws -> (oracle, device stream mode).  Three comparisons:
       * the demodulated rx samples BEFORE detection (OFDM.demodulate output per rx antenna) at `rel`
         (float32: 1e-5 for every antenna shape) of max(|ref|, rms);
-      * the equalised symbols: SISO at `rel` of max(|ref|, rms); MIMO float32 at the per-subcarrier
-        first-order bound rel * ||G_k|| (||y_k|| + ||H_k|| ||z_k||) (gpu_util.mimo_eq_tolerance) — the
-        receive filter amplifies the 1e-5 of its inputs by its norm;
+      * the equalised symbols: float64 at `rel` of max(|ref|, rms); float32 at the per-subcarrier first-order
+        bound rel * ||G_k|| (||y_k|| + ||H_k|| ||z_k||) (gpu_util.eq_tolerance; SISO: G_k = 1 / H_k) — the
+        receive filter / one-tap division amplifies the 1e-5 of its inputs by its norm, which is what makes
+        a deep fade (|H_k| ~ 1e-3) look like a 5e-5 "relative" error on a symbol of magnitude 50;
       * the decisions: identical (exact), or any mismatch has an oracle margin below `eps`
-        (float32 MIMO: below 4x that symbol's sample bound)."""
+        (float32: below 4x that symbol's sample bound at DEC_REL, i.e. a few times the measured error)."""
     f32 = link.dtype == 0
     npdt = np.float32 if f32 else np.float64
     idx, phi, psi, noise = OL.draws_ofdm_tdl(cfg, SEED, units, dtype=npdt)
@@ -54,18 +56,18 @@ def run_stream_vs_oracle(cfg, link, units, exact, rel, eps=2e-4):
     ref_hat = np.empty_like(idx)
     ref_eq = np.empty(idx.shape, dtype=complex)
     ref_rx = np.empty((n, cfg.Nr, cfg.n_sym * cfg.used), dtype=complex)
-    tol_eq = np.empty(idx.shape) if (cfg.mimo and f32) else None
+    tol_eq = np.empty(idx.shape) if f32 else None
     for u in range(n):
         ref_hat[u], det = OL.ofdm_tdl_frame(cfg, idx[u], phi[u].astype(np.float64), psi[u].astype(np.float64),
                                             noise[u].astype(np.complex128), detail=True)
         ref_eq[u] = det['eq']
         ref_rx[u] = det['Y']
         if tol_eq is not None:
-            tol_eq[u] = mimo_eq_tolerance(det, rel, cfg.Nr, cfg.Nt)
+            tol_eq[u] = eq_tolerance(det, rel, cfg.Nr, cfg.Nt)
     worst_rx = assert_samples_close(_t(rx), ref_rx, rel, 'rx samples before detection')
     worst_eq = assert_samples_close(_t(eq), ref_eq, rel, 'equalised symbols', tol=tol_eq)
     if tol_eq is not None:
-        eps = 4.0 * tol_eq
+        eps = 4.0 * tol_eq * (DEC_REL / rel)
     nbad = assert_decisions(_t(hat), ref_hat, cfg.modem, ref_eq, exact=exact, eps=eps)
     ref_cnt = OL.counters(idx, ref_hat, cfg.modem.bits)
     assert abs(int(cnt[0]) - int(ref_cnt[0])) <= nbad and abs(int(cnt[1]) - int(ref_cnt[1])) <= 8 * nbad
@@ -162,7 +164,7 @@ def test_f32_within_tolerance(case, jakes):
     # 1e-5 relative on samples (BASELINE north_star) at every antenna shape: rx samples before detection and SISO
     # equalised symbols directly, MIMO equalised symbols through the per-subcarrier ||G_k|| bound.  SISO decision
     # mismatches must sit within 4x the worst equalised-sample error (1e-5 x |z| <~ 1.5) of a boundary.
-    run_stream_vs_oracle(cfg, link, np.arange(50, 53), exact=False, rel=REL_F32, eps=1e-4)
+    run_stream_vs_oracle(cfg, link, np.arange(50, 53), exact=False, rel=REL_F32)
 
 
 @pytest.mark.parametrize('case,nframes', [
@@ -174,7 +176,7 @@ def test_f32_bench_kernels_64_frames(case, nframes):
     """The three float32 kernels bench.py times (frame-pair, antenna-pair 2x2, antenna-pair 4x4) against the
     float64 oracle on 64 full-size frames each (131 k / 131 k / 524 k symbols)."""
     cfg, link = make_pair(dtype='f32', **case)
-    run_stream_vs_oracle(cfg, link, np.arange(1000, 1000 + nframes), exact=False, rel=REL_F32, eps=1e-4)
+    run_stream_vs_oracle(cfg, link, np.arange(1000, 1000 + nframes), exact=False, rel=REL_F32)
 
 
 @pytest.mark.parametrize('case', [
@@ -189,7 +191,7 @@ def test_f32_pair_kernels_guard_band(case):
     import torch
     from pyphysim_b200 import links
     cfg, pair = make_pair(dtype='f32', **case)
-    run_stream_vs_oracle(cfg, pair, np.arange(20, 23), exact=False, rel=REL_F32, eps=1e-4)
+    run_stream_vs_oracle(cfg, pair, np.arange(20, 23), exact=False, rel=REL_F32)
     gen = links.OfdmTdlLink(pair.modulator, cfg.fft, cfg.cp, cfg.used, Nr=cfg.Nr, Nt=cfg.Nt,
                             tap_powers_linear=cfg.tap_powers, tap_delays=cfg.delays, Fd=10.0, Ts=cfg.Ts, L=20,
                             t0=cfg.t0, noise_var=cfg.noise_var, dtype='f32', seed=SEED, use_pair_kernel=False)
@@ -243,7 +245,7 @@ def test_pair_kernel_vs_generic_kernel(ant, fft, cp, nsym):
     c_f, hat_f = pair.run(n, first_unit=300, want_idx=True)
     assert np.array_equal(c_f, c_p) and torch.equal(hat_f, hat_p)            # fused == stream, pair kernel
     # oracle, one frame (full-size frames are slow in NumPy)
-    run_stream_vs_oracle(cfg, pair, np.arange(300, 301), exact=False, rel=REL_F32, eps=1e-4)
+    run_stream_vs_oracle(cfg, pair, np.arange(300, 301), exact=False, rel=REL_F32)
 
 
 @pytest.mark.parametrize('mod,M,fft,cp,nsym,n', [('qam', 64, 1024, 72, 1, 13), ('psk', 8, 2048, 144, 2, 6),
@@ -271,7 +273,7 @@ def test_frame_pair_kernel_vs_generic_kernel(mod, M, fft, cp, nsym, n):
     assert np.array_equal(c_f, c_p) and torch.equal(hat_f, hat_p)
     c_n = pair.run(n, first_unit=500)                                        # counters only, no outputs
     assert np.array_equal(c_n, c_p)
-    run_stream_vs_oracle(cfg, pair, np.arange(500, 502), exact=False, rel=REL_F32 if cp else 3e-5, eps=2e-4)
+    run_stream_vs_oracle(cfg, pair, np.arange(500, 502), exact=False, rel=REL_F32)
 
 
 @pytest.mark.parametrize('n,first', [(1, 0), (7, 0), (7, 3), (20, 11)])
