@@ -103,6 +103,9 @@ int b200phy_version(void);
 const char *b200phy_last_error(void);
 /* number of kernels this library has launched in the calling process (bench `gpu_launches`) */
 uint64_t b200phy_launch_count(void);
+/* "name<template arguments>" of the fused-link kernel instantiation launched last (process-wide; bench.py
+ * checks it against the kernel name in the committed ncu capture before it quotes that capture) */
+const char *b200phy_last_kernel(void);
 
 /* ---- stage ops (API-parity path behind the façade classes) ---------------------- */
 

@@ -48,6 +48,7 @@ SIGNATURES = {
     'b200phy_version': (C.c_int, []),
     'b200phy_last_error': (C.c_char_p, []),
     'b200phy_launch_count': (C.c_uint64, []),
+    'b200phy_last_kernel': (C.c_char_p, []),
     'b200phy_map': (C.c_int, [C.c_int, _MP, _vp, C.c_int64, _vp, _vp, _vp]),
     'b200phy_demap': (C.c_int, [C.c_int, _MP, _vp, C.c_int64, _vp, _vp]),
     'b200phy_count_errors': (C.c_int, [_vp, _vp, C.c_int64, _vp, _vp]),

@@ -151,6 +151,7 @@ __device__ __forceinline__ void flush_counters(unsigned sym_err, unsigned bit_er
 void set_error(const char *fmt, ...);
 int check_cuda(cudaError_t e, const char *what);
 void count_launch(int n = 1);
+void note_kernel(const char *fmt, ...);   // name<template arguments> of the fused-link kernel just launched
 int check_modem(const b200phy_modem *m, Modem *out);
 
 // Stream-mode kernels use vector loads / stores: a base pointer that is not aligned to `a` bytes (a sliced

@@ -25,6 +25,14 @@ int check_cuda(cudaError_t e, const char *what) {
 
 void count_launch(int n) { g_launches.fetch_add(uint64_t(n), std::memory_order_relaxed); }
 
+static char g_last_kernel[160] = "";
+void note_kernel(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_last_kernel, sizeof(g_last_kernel), fmt, ap);
+    va_end(ap);
+}
+
 int check_modem(const b200phy_modem *m, Modem *out) {
     if (!m) { set_error("modem is NULL"); return B200PHY_ERR_INVALID; }
     const int M = m->M;
@@ -57,4 +65,5 @@ extern "C" {
 int b200phy_version(void) { return B200PHY_VERSION; }
 const char *b200phy_last_error(void) { return b200phy::g_err; }
 uint64_t b200phy_launch_count(void) { return b200phy::g_launches.load(); }
+const char *b200phy_last_kernel(void) { return b200phy::g_last_kernel; }
 }

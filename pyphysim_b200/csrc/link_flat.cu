@@ -383,6 +383,7 @@ static int launch_siso_flat(const Modem &m, const void *table, int rayleigh, dou
     else { if (rayleigh) B200_SISO2(false, true); else B200_SISO2(false, false); }
 #undef B200_SISO2
 #undef B200_SISO3
+    note_kernel("siso_flat_kernel<%s,%d,%d,%d,%d>", sizeof(T) == 4 ? "float" : "double", int(fused), int(rayleigh != 0), int(qam), int(dec != nullptr));
     B200_CHECK_LAUNCH("siso_flat_kernel");
     return B200PHY_OK;
 }
@@ -408,6 +409,7 @@ static int launch_alamouti(const Modem &m, const void *table, int Nr, int S, dou
 #undef B200_ALA
 #undef B200_ALA2
 #undef B200_ALA3
+    note_kernel("alamouti_kernel<%s,%d,%d,%d,%d>", sizeof(T) == 4 ? "float" : "double", int(fused), Nr > 3 ? 4 : Nr, int(dec != nullptr), int(qpsk));
     B200_CHECK_LAUNCH("alamouti_kernel");
     return B200PHY_OK;
 }

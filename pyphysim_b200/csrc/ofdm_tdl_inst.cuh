@@ -38,6 +38,7 @@ static int launch_one(const OfdmP &p, const Modem &m, const void *table, uint64_
                                        (const T *)phi, (const T *)psi, (const cx<T> *)noise, idx_hat,
                                        (cx<T> *)eq_out, ws, (unsigned long long *)counters);
     count_launch();
+    note_kernel("ofdm_tdl_kernel<%s,%d,%d,%d,%d>", sizeof(T) == 4 ? "float" : "double", int(FUSED), NR, NT, int(WSG));
     e = check_cuda(cudaGetLastError(), "ofdm_tdl_kernel launch");
     if (WSG) cudaFreeAsync(ws, st);
     return e;
@@ -72,6 +73,7 @@ static int launch_pair_kt(const OfdmP &p, const Modem &m, const void *table, uin
                                       (const float *)phi, (const float *)psi, (const cx<float> *)noise,
                                       idx_hat, (cx<float> *)eq_out, (unsigned long long *)counters);
     count_launch();
+    note_kernel("ofdm_tdl_pair_kernel<%d,%d,%d,%d,%d,%d>", int(FUSED), NR, NT, int(QAMK), KT, LGF);
     return check_cuda(cudaGetLastError(), "ofdm_tdl_pair_kernel launch");
 }
 
@@ -129,6 +131,7 @@ static int launch_fpair_kl(const OfdmP &p, const Modem &m, const void *table, ui
                                        (const float *)phi, (const float *)psi, (const cx<float> *)noise,
                                        idx_hat, (cx<float> *)eq_out, (unsigned long long *)counters);
     count_launch();
+    note_kernel("ofdm_tdl_fpair_kernel<%d,%d,%d>", int(FUSED), int(QAMK), LGF);
     return check_cuda(cudaGetLastError(), "ofdm_tdl_fpair_kernel launch");
 }
 
