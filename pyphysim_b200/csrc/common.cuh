@@ -43,6 +43,27 @@ template <typename T> __device__ __forceinline__ cx<T> cdiv(cx<T> a, cx<T> b) {
 }
 template <typename T, typename S> __device__ __forceinline__ cx<T> cvt(cx<S> a) { return {T(a.re), T(a.im)}; }
 
+// ---- packed FP32 pairs (Blackwell FFMA2: fma.rn.f32x2).  One instruction issues two FMAs; a scalar
+// operand written as pk2(s, s) is folded by ptxas into a broadcast operand (no MOVs), so an issue-bound
+// loop halves its issue slots.  Same rounding as two scalar fmaf.
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pk2(float lo, float hi) {
+    u64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk2(u64 v, float &lo, float &hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
+    u64 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ u64 sub2(u64 a, u64 b) { u64 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+
 // ---------------------------------------------------------------- constellations
 // Device view of a modulator (Modulator.symbols + how to slice it).
 struct Modem {

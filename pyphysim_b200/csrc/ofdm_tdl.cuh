@@ -207,23 +207,7 @@ __device__ __forceinline__ void tap_mac(cx<T> &acc, const cx<T> (&cf)[4], T tau,
     cmac(acc, g, x);
 }
 
-// ---- packed FP32 pairs (Blackwell FFMA2: fma.rn.f32x2).  One instruction issues two FMAs; a scalar
-// operand written as pk2(s, s) is folded by ptxas into a broadcast operand (no MOVs), so the FIR inner
-// loop halves its issue slots.  Same rounding as two scalar fmaf.
-typedef unsigned long long u64;
-__device__ __forceinline__ u64 pk2(float lo, float hi) {
-    u64 r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ void upk2(u64 v, float &lo, float &hi) {
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) {
-    u64 d;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-    return d;
-}
+// (packed FP32 pair helpers pk2 / upk2 / fma2 / add2 / sub2 / mul2: common.cuh)
 
 // S[C] += gbar_l[r][t] * w for the residue class C = d_l mod 4 of a tap
 template <typename T, int NR, int NT, int C>

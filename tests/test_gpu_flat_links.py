@@ -119,6 +119,56 @@ def test_host_entry_point_matches_device_path():
 
 
 # ------------------------------------------------------------------ C4: Alamouti
+@pytest.mark.parametrize('kind,M', [('qpsk', 4), ('qam', 16)])
+def test_alamouti_c4_f32_kernel(kind, M):
+    """The compile-time-shape float32 kernel of the C4 shape (Nr = 2, one codeword): stream mode == fused mode on
+    the device's own draws (one arithmetic for both), == the host-buffer entry point in both modes, samples within
+    1e-5 of the oracle, mismatches only on decision boundaries; misaligned tensors are refused, not faulted on."""
+    from pyphysim_b200 import links
+    import torch
+    pm, om = product_modem(kind, M), oracle_modem(kind, M)
+    n, nv = 50001, 1 / md.dB2Linear(9.0)
+    d = links.draw_flat_mimo(pm, n, Nr=2, Nt=2, num_symbols=2, n_data=2, seed=SEED, first_unit=77, dtype='f32')
+    c_s, hat_s, dec_s = links.link_alamouti(pm, nv, n, draws=d, dtype='f32', want_idx=True, want_samples=True)
+    c_f, hat_f = links.link_alamouti(pm, nv, n, seed=SEED, first_unit=77, dtype='f32', want_idx=True)
+    assert np.array_equal(c_s, c_f) and torch.equal(hat_s, hat_f)
+    c_n = links.link_alamouti(pm, nv, n, draws=d, dtype='f32')              # no outputs: QPSK skips the gain
+    assert np.array_equal(c_n, c_s)
+    ref_hat, ref_dec = OL.alamouti(om, _t(d[0]).astype(np.int64), _t(d[1]).astype(complex), _t(d[2]).astype(complex), nv)
+    assert_samples_close(_t(dec_s), ref_dec, 1e-5, 'alamouti22 f32')
+    assert_decisions(_t(hat_s), ref_hat, om, ref_dec, exact=False, eps=2e-5, what='alamouti22 f32')
+    host = tuple(t.cpu().pin_memory() for t in d)
+    c_h, hat_h = links.link_alamouti_host(pm, nv, n, draws=host, dtype='f32', want_idx=True)
+    assert np.array_equal(c_h, c_s) and np.array_equal(hat_h.numpy(), _t(hat_s))
+    assert np.array_equal(links.link_alamouti_host(pm, nv, n, seed=SEED, first_unit=77, dtype='f32'), c_s)
+    with pytest.raises(ValueError, match='aligned'):
+        links.link_alamouti(pm, nv, 8, draws=(d[0][:8], d[1].view(torch.float32).reshape(-1)[2:2 + 64].view(torch.complex64),
+                                               d[2][:8]), dtype='f32')
+
+
+def test_blast_and_precoded_host_entry_points():
+    from pyphysim_b200 import links
+    pm = product_modem('qam', 16)
+    n, nv = 20001, 0.02
+    d = links.draw_flat_mimo(pm, n, Nr=2, Nt=2, num_symbols=3, n_data=6, seed=SEED, dtype='f32')
+    c_dev, hat_dev = links.link_blast(pm, nv, n, Nr=2, Nt=2, num_symbols=3, filter_noise_var=nv, draws=d, dtype='f32',
+                                      want_idx=True)
+    host = tuple(t.cpu().pin_memory() for t in d)
+    c_h, hat_h = links.link_blast_host(pm, nv, n, Nr=2, Nt=2, num_symbols=3, filter_noise_var=nv, draws=host,
+                                       dtype='f32', want_idx=True)
+    assert np.array_equal(c_h, c_dev) and np.array_equal(hat_h.numpy(), _t(hat_dev))
+    assert np.array_equal(links.link_blast_host(pm, nv, n, Nr=2, Nt=2, num_symbols=3, filter_noise_var=nv, seed=SEED,
+                                                dtype='f32'), c_dev)
+    d = links.draw_flat_mimo(pm, n, Nr=4, Nt=4, num_symbols=2, n_data=8, seed=SEED, dtype='f32')
+    for scheme in ('svd', 'gmd'):
+        c_dev = links.link_precoded(pm, nv, n, scheme=scheme, Nr=4, Nt=4, num_symbols=2, draws=d, dtype='f32')
+        c_h = links.link_precoded_host(pm, nv, n, scheme=scheme, Nr=4, Nt=4, num_symbols=2,
+                                       draws=tuple(t.cpu() for t in d), dtype='f32')
+        assert np.array_equal(c_h, c_dev)
+        assert np.array_equal(links.link_precoded_host(pm, nv, n, scheme=scheme, Nr=4, Nt=4, num_symbols=2, seed=SEED,
+                                                       dtype='f32'), c_dev)
+
+
 @pytest.mark.parametrize('Nr,S,kind,M', [(2, 2, 'qpsk', 4), (1, 4, 'qam', 16), (3, 6, 'psk', 8)])
 def test_alamouti_f64_bit_exact_vs_oracle(Nr, S, kind, M):
     from pyphysim_b200 import links
