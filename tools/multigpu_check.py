@@ -42,12 +42,38 @@ def main():
     f3, n3 = D.shard(10 ** 7 + 1)
     links.link_siso_flat(QAM(64), 0.03, n3, first_unit=f3, counters=c3)
     D.allreduce_counters(c3)
+    # SISO OFDM in float32 (frame-pair kernel) with an odd total: the shards are odd-sized and start at odd units,
+    # so frames change lane / pair partner / masked-tail status between the sharded and the single-GPU run
+    siso = links.OfdmTdlLink(QAM(64), 1024, 72, 1024, tap_powers_linear=prof.tap_powers_linear,
+                             tap_delays=prof.tap_delays, Fd=10.0, Ts=Ts, L=20, noise_var=0.01, seed=78)
+    c4 = torch.zeros(4, dtype=torch.int64, device='cuda')
+    f4, n4 = D.shard(20003, first_unit=1)
+    siso.run(n4, first_unit=f4, counters=c4)
+    D.allreduce_counters(c4)
+    # the Monte Carlo runner: every rank drives the same LinkSimulationRunner, results must agree with 1 GPU
+    from pyphysim_b200.simulations import LinkSimulationRunner
+
+    def mc(nv, f0, n):
+        link.set_noise_var(nv)
+        return link.run_host(n, first_unit=f0)
+    runner = LinkSimulationRunner(mc, 6001, [20.0, 25.0], rep_max=2)
+    runner.simulate()
+    r_se = runner.results.get_result_values_list('symbol_errors')
     torch.cuda.synchronize()
     if rank == 0:
+        link.set_noise_var(0.003)                  # the runner above walked the SNR points on this link object
         ref = link.run(total, first_unit=500)
         ref2 = links.link_alamouti(QPSK(), 0.1, 10 ** 7 + 3)
         ref3 = links.link_siso_flat(QAM(64), 0.03, 10 ** 7 + 1)
-        for name, a, b in (('ofdm2x2', c, ref), ('alamouti', c2, ref2), ('siso', c3, ref3)):
+        ref4 = siso.run(20003, first_unit=1)
+        ref_se = []
+        for snr in (20.0, 25.0):
+            link.set_noise_var(10 ** (-snr / 10))
+            ref_se.append(int(link.run(2 * 6001)[0]))
+        same = r_se == ref_se
+        ok &= same
+        print('runner    world=%d sharded=%s single=%s %s' % (world, r_se, ref_se, 'OK' if same else 'MISMATCH'))
+        for name, a, b in (('ofdm2x2', c, ref), ('alamouti', c2, ref2), ('siso', c3, ref3), ('ofdm_siso_f32_odd', c4, ref4)):
             same = np.array_equal(a.cpu().numpy(), b)
             ok &= same
             print('%-9s world=%d sharded=%s single=%s %s' % (name, world, a.cpu().numpy().tolist(), list(b),
