@@ -51,7 +51,7 @@ def build(force=False, verbose=False, extra_flags=(), lib_path=None, obj_dir=Non
     LIB = lib_path or globals()['LIB']
     OBJ = obj_dir or globals()['OBJ']
     os.makedirs(OBJ, exist_ok=True)
-    stamp = os.path.join(OBJ, 'digest')
+    stamp = LIB + '.digest'          # next to the library: it travels with it (the object directory does not)
     dig = _digest() + ' '.join(extra_flags)
     if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read() == dig:
         return LIB

@@ -82,7 +82,7 @@ __device__ __forceinline__ int siso_one(const Modem &m, const cx<T> *tab, int a,
 
 template <typename T, bool FUSED, bool RAYLEIGH, bool QAM, bool DEC>
 __global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 5 : 2)
-siso_flat_kernel(Modem m_in, const cx<T> *__restrict__ tab_g, T sigma, uint64_t seed,
+siso_flat_kernel(Modem m_in, const cx<T> *__restrict__ tab_g, T sigma, const __grid_constant__ PhiloxKey seed,
                  uint64_t first_unit, long long n, const uint8_t *__restrict__ idx,
                  const cx<T> *__restrict__ h, const cx<T> *__restrict__ noise,
                  uint8_t *__restrict__ idx_hat, cx<T> *__restrict__ dec_out,
@@ -154,7 +154,7 @@ siso_flat_kernel(Modem m_in, const cx<T> *__restrict__ tab_g, T sigma, uint64_t 
 // One realization per thread: H[Nr][2], S symbols (S/2 codewords), noise[Nr][S].
 template <typename T, bool FUSED, int NR, bool DEC, bool QPSK>
 __global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 5 : 2)
-alamouti_kernel(Modem m_in, const cx<T> *__restrict__ tab_g, int S, T sigma, uint64_t seed,
+alamouti_kernel(Modem m_in, const cx<T> *__restrict__ tab_g, int S, T sigma, const __grid_constant__ PhiloxKey seed,
                 uint64_t first_unit, long long n, const uint8_t *__restrict__ idx,
                 const cx<T> *__restrict__ Hg, const cx<T> *__restrict__ noise,
                 uint8_t *__restrict__ idx_hat, cx<T> *__restrict__ dec_out,
@@ -249,7 +249,7 @@ alamouti_kernel(Modem m_in, const cx<T> *__restrict__ tab_g, int S, T sigma, uin
 // different 128-bit loads, so every pair costs two register moves and the instruction count did not drop.)
 template <bool FUSED, bool DEC, bool QPSK>
 __global__ void __launch_bounds__(kThreads, 5)
-alamouti22_kernel(Modem m_in, const cx<float> *__restrict__ tab_g, float sigma, uint64_t seed, uint64_t first_unit,
+alamouti22_kernel(Modem m_in, const cx<float> *__restrict__ tab_g, float sigma, const __grid_constant__ PhiloxKey seed, uint64_t first_unit,
                   long long n, const uint8_t *__restrict__ idx, const float4 *__restrict__ Hg,
                   const float4 *__restrict__ noise, uint8_t *__restrict__ idx_hat, cx<float> *__restrict__ dec_out,
                   unsigned long long *counters) {
@@ -322,7 +322,7 @@ alamouti22_kernel(Modem m_in, const cx<float> *__restrict__ tab_g, float sigma, 
 template <typename T, bool FUSED, int NT>
 __global__ void __launch_bounds__(kThreads)
 blast_kernel(Modem m, const cx<T> *__restrict__ tab_g, int Nr, int S, T sigma, double fnv,
-             uint64_t seed, uint64_t first_unit, long long n, const uint8_t *__restrict__ idx,
+             const __grid_constant__ PhiloxKey seed, uint64_t first_unit, long long n, const uint8_t *__restrict__ idx,
              const cx<T> *__restrict__ Hg, const cx<T> *__restrict__ noise,
              uint8_t *__restrict__ idx_hat, cx<T> *__restrict__ dec_out,
              unsigned long long *counters) {
@@ -396,7 +396,7 @@ blast_kernel(Modem m, const cx<T> *__restrict__ tab_g, int Nr, int S, T sigma, d
 
 // ================================================================= draw dumps
 template <typename T>
-__global__ void draw_siso_flat_kernel(int bits, uint64_t seed, uint64_t first_unit, long long n,
+__global__ void draw_siso_flat_kernel(int bits, const __grid_constant__ PhiloxKey seed, uint64_t first_unit, long long n,
                                       uint8_t *idx, cx<T> *h, cx<T> *noise) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
          i += (long long)gridDim.x * blockDim.x) {
@@ -408,7 +408,7 @@ __global__ void draw_siso_flat_kernel(int bits, uint64_t seed, uint64_t first_un
 }
 
 template <typename T>
-__global__ void draw_flat_mimo_kernel(int bits, int Nr, int Nt, int S, int n_data, uint64_t seed,
+__global__ void draw_flat_mimo_kernel(int bits, int Nr, int Nt, int S, int n_data, const __grid_constant__ PhiloxKey seed,
                                       uint64_t first_unit, long long n, uint8_t *idx, cx<T> *H,
                                       cx<T> *noise) {
     const int row = 2 * ((S + 1) / 2);

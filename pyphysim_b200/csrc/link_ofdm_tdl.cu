@@ -122,7 +122,7 @@ static int fill_params(const b200phy_ofdm_tdl_params *q, const Modem &m, OfdmP *
 
 // ---------------------------------------------------------------- draw dump
 template <typename T>
-__global__ void draw_ofdm_tdl_kernel(OfdmP p, int bits, int NR, uint64_t first_unit, long long n_units,
+__global__ void draw_ofdm_tdl_kernel(const __grid_constant__ OfdmP p, int bits, int NR, uint64_t first_unit, long long n_units,
                                      uint8_t *idx, T *phi, T *psi, cx<T> *noise) {
     const long long rowlen = p.N + p.mem;
     for (long long frame = blockIdx.x; frame < n_units; frame += gridDim.x) {

@@ -151,7 +151,7 @@ mat_apply_kernel(const cx<T> *__restrict__ A, int rows, int cols, const cx<T> *_
 // Symbol p = l * S + s of a realization is layer l at time s (X = transmit_data.reshape(Nt, -1)).
 template <typename T, bool FUSED, int N, int SCHEME>
 __global__ void __launch_bounds__(kPT)
-precoded_kernel(Modem m, const cx<T> *__restrict__ tab_g, int S, T sigma, double fnv, uint64_t seed,
+precoded_kernel(Modem m, const cx<T> *__restrict__ tab_g, int S, T sigma, double fnv, const __grid_constant__ PhiloxKey seed,
                 uint64_t first_unit, long long n, const uint8_t *__restrict__ idx,
                 const cx<T> *__restrict__ Hg, const cx<T> *__restrict__ noise,
                 uint8_t *__restrict__ idx_hat, cx<T> *__restrict__ dec_out, unsigned long long *counters) {
@@ -273,7 +273,7 @@ precoded_kernel(Modem m, const cx<T> *__restrict__ tab_g, int S, T sigma, double
 // MRT (mimo.py:666-783): one receive antenna, one layer; W = conj(h) / |h| / sqrt(Nt), G = sqrt(Nt) / sum |h|
 template <typename T, bool FUSED, int NT>
 __global__ void __launch_bounds__(256)
-mrt_kernel(Modem m, const cx<T> *__restrict__ tab_g, int S, T sigma, uint64_t seed, uint64_t first_unit,
+mrt_kernel(Modem m, const cx<T> *__restrict__ tab_g, int S, T sigma, const __grid_constant__ PhiloxKey seed, uint64_t first_unit,
            long long n, const uint8_t *__restrict__ idx, const cx<T> *__restrict__ Hg,
            const cx<T> *__restrict__ noise, uint8_t *__restrict__ idx_hat, cx<T> *__restrict__ dec_out,
            unsigned long long *counters) {

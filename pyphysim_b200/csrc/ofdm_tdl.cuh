@@ -54,7 +54,7 @@ struct OfdmP {
     double Ts1;     // Ts * 1.0000000001 (fading_generators.py:462)
     double t0;
     double sigma, fnv, tx_scale, rx_scale, snt;
-    uint64_t seed;
+    PhiloxKey seed;              // round keys of the 64-bit seed (rng.cuh)
     void *rx_out;   // optional: demodulated rx samples before detection, complex[n][Nr][n_sym*used] (parity tests)
 };
 

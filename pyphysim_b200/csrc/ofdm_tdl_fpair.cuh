@@ -121,11 +121,10 @@ ofdm_tdl_fpair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const c
                 const uint64_t unit = first_unit + uint64_t(ln ? frameB : frame);
                 const uint4 b1 = rng_block(p.seed, STREAM_CHANNEL, unit, uint64_t(b));
                 const uint4 b2 = rng_block(p.seed, STREAM_CHANNEL, unit, uint64_t((p.P4 >> 2) + b));
-#pragma unroll
-                for (int l = 0; l < 4; ++l) {
-                    ph_phi[ln * p.P4 + 4 * b + l] = phase_from_word<T>(lane_of(b1, l));
-                    ph_psi[ln * p.P4 + 4 * b + l] = phase_from_word<T>(lane_of(b2, l));
-                }
+                reinterpret_cast<float4 *>(ph_phi + ln * p.P4)[b] = make_float4(phase_from_word<T>(b1.x), phase_from_word<T>(b1.y),
+                                                                                phase_from_word<T>(b1.z), phase_from_word<T>(b1.w));
+                reinterpret_cast<float4 *>(ph_psi + ln * p.P4)[b] = make_float4(phase_from_word<T>(b2.x), phase_from_word<T>(b2.y),
+                                                                                phase_from_word<T>(b2.z), phase_from_word<T>(b2.w));
             }
         } else if (pf) {
             cp_async_wait<0>();                      // prefetched during the previous pair
@@ -164,14 +163,22 @@ ofdm_tdl_fpair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const c
                 }
                 const int m0 = n_s + cp;
                 if constexpr (FUSED) {
+                    // one thread draws sample pair (j, j + 1) of BOTH frames: two independent Philox chains per
+                    // iteration and whole pair samples (one 16-byte store each) instead of scalar stores
                     const int pr0 = m0 >> 1, npr = ((m0 + fft - 1) >> 1) - pr0 + 1;
-                    for (int it = tid; it < 2 * npr; it += kOT) {
-                        const int ln = it / npr, q = pr0 + it - ln * npr;
-                        const uint4 blk = rng_block(p.seed, STREAM_NOISE, first_unit + uint64_t(ln ? frameB : frame), uint64_t(q));
-                        const int j = 2 * q - m0;
-                        float *yr = reinterpret_cast<float *>(Y) + ln;
-                        if (j >= 0 && j < fft) { const cx<T> c = sigma * cnormal<T>(blk.x, blk.y); yr[4 * j] = c.re; yr[4 * j + 2] = c.im; }
-                        if (j + 1 >= 0 && j + 1 < fft) { const cx<T> c = sigma * cnormal<T>(blk.z, blk.w); yr[4 * j + 4] = c.re; yr[4 * j + 6] = c.im; }
+                    const uint64_t uA = first_unit + uint64_t(frame), uB = first_unit + uint64_t(frameB);
+                    for (int i = tid; i < npr; i += kOT) {
+                        const int q = pr0 + i, j = 2 * q - m0;
+                        const uint4 b0 = rng_block(p.seed, STREAM_NOISE, uA, uint64_t(q));
+                        const uint4 b1 = rng_block(p.seed, STREAM_NOISE, uB, uint64_t(q));
+                        if (j >= 0 && j < fft) {
+                            const cx<T> c0 = sigma * cnormal<T>(b0.x, b0.y), c1 = sigma * cnormal<T>(b1.x, b1.y);
+                            Y[j] = make_float4(c0.re, c1.re, c0.im, c1.im);
+                        }
+                        if (j + 1 >= 0 && j + 1 < fft) {
+                            const cx<T> c0 = sigma * cnormal<T>(b0.z, b0.w), c1 = sigma * cnormal<T>(b1.z, b1.w);
+                            Y[j + 1] = make_float4(c0.re, c1.re, c0.im, c1.im);
+                        }
                     }
                 } else if (apipe) {
                     const size_t rowlen = size_t(p.N + mem);

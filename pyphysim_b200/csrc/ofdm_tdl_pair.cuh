@@ -353,11 +353,10 @@ ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const cx
             for (int b = tid; b < (p.P4 >> 2); b += KT) {
                 const uint4 b1 = rng_block(p.seed, STREAM_CHANNEL, unit, uint64_t(b));
                 const uint4 b2 = rng_block(p.seed, STREAM_CHANNEL, unit, uint64_t((p.P4 >> 2) + b));
-#pragma unroll
-                for (int l = 0; l < 4; ++l) {
-                    ph_phi[4 * b + l] = phase_from_word<T>(lane_of(b1, l));
-                    ph_psi[4 * b + l] = phase_from_word<T>(lane_of(b2, l));
-                }
+                reinterpret_cast<float4 *>(ph_phi)[b] = make_float4(phase_from_word<T>(b1.x), phase_from_word<T>(b1.y),
+                                                                    phase_from_word<T>(b1.z), phase_from_word<T>(b1.w));
+                reinterpret_cast<float4 *>(ph_psi)[b] = make_float4(phase_from_word<T>(b2.x), phase_from_word<T>(b2.y),
+                                                                    phase_from_word<T>(b2.z), phase_from_word<T>(b2.w));
             }
         } else if (pf) {
             cp_async_wait<0>();                      // prefetched during the previous frame (visible after the barrier below)
@@ -384,12 +383,22 @@ ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const cx
                 const int w0 = s * used * NT, cnt = used * NT;
                 if constexpr (FUSED) {
                     const int b0 = w0 >> 2, b1 = (w0 + cnt - 1) >> 2;
-                    for (int b = b0 + tid; b <= b1; b += KT) {
-                        const uint4 blk = rng_block(p.seed, STREAM_DATA, unit, uint64_t(b));
+                    if (((w0 | cnt) & 3) == 0) {
+                        // whole blocks: the four symbols of a Philox block are one 32-bit store
+                        const int sh = 32 - m.bits;
+                        for (int b = b0 + tid; b <= b1; b += KT) {
+                            const uint4 blk = rng_block(p.seed, STREAM_DATA, unit, uint64_t(b));
+                            reinterpret_cast<uint32_t *>(dsym)[b - b0] =
+                                (blk.x >> sh) | ((blk.y >> sh) << 8) | ((blk.z >> sh) << 16) | ((blk.w >> sh) << 24);
+                        }
+                    } else {
+                        for (int b = b0 + tid; b <= b1; b += KT) {
+                            const uint4 blk = rng_block(p.seed, STREAM_DATA, unit, uint64_t(b));
 #pragma unroll
-                        for (int l = 0; l < 4; ++l) {
-                            const int w = 4 * b + l - w0;
-                            if (w >= 0 && w < cnt) dsym[w] = uint8_t(lane_of(blk, l) >> (32 - m.bits));
+                            for (int l = 0; l < 4; ++l) {
+                                const int w = 4 * b + l - w0;
+                                if (w >= 0 && w < cnt) dsym[w] = uint8_t(lane_of(blk, l) >> (32 - m.bits));
+                            }
                         }
                     }
                 } else if (!pf) {
@@ -404,15 +413,24 @@ ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const cx
                 }
                 const int m0 = n_s + cp;
                 if constexpr (FUSED) {
+                    // one thread draws sample pair (j, j + 1) of BOTH antennas of an rx pair: two independent Philox
+                    // chains per iteration and whole pair samples (one 16-byte store each) instead of scalar stores
                     const int pr0 = m0 >> 1, npr = ((m0 + fft - 1) >> 1) - pr0 + 1;
-                    for (int it = tid; it < NR * npr; it += KT) {
-                        const int r = it / npr, pr = pr0 + it % npr;
-                        const uint4 blk = rng_block(p.seed, STREAM_NOISE, unit, uint64_t(r) * (p.row >> 1) + pr);
-                        const int j = 2 * pr - m0;
-                        float *yr = reinterpret_cast<float *>(pick(Yp, r >> 1)) + (r & 1);
-                        if (j >= 0 && j < fft) { const cx<T> c = sigma * cnormal<T>(blk.x, blk.y); yr[4 * j] = c.re; yr[4 * j + 2] = c.im; }
-                        if (j + 1 >= 0 && j + 1 < fft) { const cx<T> c = sigma * cnormal<T>(blk.z, blk.w); yr[4 * j + 4] = c.re; yr[4 * j + 6] = c.im; }
-                    }
+#pragma unroll
+                    for (int q = 0; q < NP; ++q)
+                        for (int i = tid; i < npr; i += KT) {
+                            const int pr = pr0 + i, j = 2 * pr - m0;
+                            const uint4 b0 = rng_block(p.seed, STREAM_NOISE, unit, uint64_t(2 * q) * (p.row >> 1) + pr);
+                            const uint4 b1 = rng_block(p.seed, STREAM_NOISE, unit, uint64_t(2 * q + 1) * (p.row >> 1) + pr);
+                            if (j >= 0 && j < fft) {
+                                const cx<T> c0 = sigma * cnormal<T>(b0.x, b0.y), c1 = sigma * cnormal<T>(b1.x, b1.y);
+                                Yp[q][j] = make_float4(c0.re, c1.re, c0.im, c1.im);
+                            }
+                            if (j + 1 >= 0 && j + 1 < fft) {
+                                const cx<T> c0 = sigma * cnormal<T>(b0.z, b0.w), c1 = sigma * cnormal<T>(b1.z, b1.w);
+                                Yp[q][j + 1] = make_float4(c0.re, c1.re, c0.im, c1.im);
+                            }
+                        }
                 } else if (apipe) {
                     // raw noise of rx 2q / 2q+1 at sample j lands in the two halves of the float4 slot j of the pair
                     // buffer (n0.re, n0.im, n1.re, n1.im); the FIR epilogue turns each slot into pair layout in
@@ -640,7 +658,10 @@ ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const cx
 
             // ---------------- F: paired FFT of every rx pair (rotating pool).  When the last pass produces exactly
             // the bins a detection thread owns, it is left to the detection phase (fft_last_pass, from registers).
-            constexpr int NU = (NR * NT <= 4) ? 4 : 2;
+#ifndef B200_PAIR_BIG_NU
+#define B200_PAIR_BIG_NU 2
+#endif
+            constexpr int NU = (NR * NT <= 4) ? 4 : B200_PAIR_BIG_NU;
             const bool fuse_last = fft_last_fusable(lg, NU);
 #pragma unroll
             for (int q = 0; q < NP; ++q) {
@@ -703,6 +724,8 @@ ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const cx
                             Hc[2][t][q] = a0 - a2;
                             Hc[3][t][q] = {sub2(a1.re, a3.im), add2(a1.im, a3.re)};      // a1 + j a3
                         }
+                } else if constexpr (NU == 1) {
+                    tap_sum(Hc[0], p.cls_start[0], p.cls_start[4]);
                 } else {
                     tap_sum(Hc[0], p.cls_start[0], p.cls_start[2]);          // even delays
                     tap_sum(Hc[1], p.cls_start[2], p.cls_start[4]);          // odd delays
@@ -719,8 +742,8 @@ ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const cx
                 ps Yv[NP][NU];
 #pragma unroll
                 for (int qq = 0; qq < NP; ++qq) {
-                    if (fuse_last) {
-                        fft_last_pass<NU>(Yp[qq], tw, fft, lg, k0, Yv[qq]);
+                    if (NU >= 2 && fuse_last) {
+                        if constexpr (NU >= 2) fft_last_pass<NU>(Yp[qq], tw, fft, lg, k0, Yv[qq]);
                     } else {
 #pragma unroll
                         for (int u = 0; u < NU; ++u) Yv[qq][u] = ld_ps(Yp[qq] + k0 + u * kstride);

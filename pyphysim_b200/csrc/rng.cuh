@@ -23,6 +23,39 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
     return c;
 }
 
+// The ten round keys of a seed, computed once on the host and passed as a kernel parameter: in the kernels
+// they are constant-bank operands of the round's LOP3, so a block costs 2 IMAD.WIDE + 2 LOP3 per round (the
+// per-thread key schedule was 18 more IADD3 per block, a third of the generator's instructions).
+struct PhiloxKey {
+    uint32_t k[20];
+    PhiloxKey() = default;
+    __host__ __device__ PhiloxKey(uint64_t seed) {
+        uint32_t a = uint32_t(seed), b = uint32_t(seed >> 32);
+        for (int i = 0; i < 10; ++i) {
+            k[2 * i] = a;
+            k[2 * i + 1] = b;
+            a += 0x9E3779B9u;
+            b += 0xBB67AE85u;
+        }
+    }
+};
+
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, const PhiloxKey &key) {
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ key.k[2 * i], lo1, hi0 ^ c.w ^ key.k[2 * i + 1], lo0);
+    }
+    return c;
+}
+
+__device__ __forceinline__ uint4 rng_block(const PhiloxKey &key, uint32_t stream, uint64_t unit, uint64_t slot) {
+    const uint4 c = make_uint4(uint32_t(slot), (stream << 16) | (uint32_t(slot >> 32) & 0xffffu),
+                               uint32_t(unit), uint32_t(unit >> 32));
+    return philox4x32_10(c, key);
+}
+
 __device__ __forceinline__ uint4 rng_block(uint64_t seed, uint32_t stream, uint64_t unit, uint64_t slot) {
     const uint4 c = make_uint4(uint32_t(slot), (stream << 16) | (uint32_t(slot >> 32) & 0xffffu),
                                uint32_t(unit), uint32_t(unit >> 32));
@@ -79,8 +112,8 @@ template <typename T> __device__ __forceinline__ cx<T> cnormal(uint32_t w0, uint
 }
 
 // complex normal number j of (stream, unit): words (2j, 2j+1)
-template <typename T>
-__device__ __forceinline__ cx<T> cnormal_at(uint64_t seed, uint32_t stream, uint64_t unit, uint64_t j) {
+template <typename T, typename K>
+__device__ __forceinline__ cx<T> cnormal_at(const K &seed, uint32_t stream, uint64_t unit, uint64_t j) {
     const uint4 b = rng_block(seed, stream, unit, j >> 1);
     return (j & 1) ? cnormal<T>(b.z, b.w) : cnormal<T>(b.x, b.y);
 }

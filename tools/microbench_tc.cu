@@ -1,0 +1,765 @@
+// microbench_tc.cu — tensor cores vs FFMA2 / DFMA for the GEMM-shaped pieces of the OFDM/TDL link
+// (SURVEY.md §7 hard part 6).  Stand-alone; prints one JSON object per experiment.
+//   build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -o /tmp/mb_tc tools/microbench_tc.cu
+//   run  : /tmp/mb_tc            (all experiments)     /tmp/mb_tc fir    (one group: raw | hk | fir | gram)
+// Experiments
+//   raw  : issue rates of mma.sync m16n8k8 tf32, m16n8k16 f16, m8n8k4 f64 against FFMA2 / DFMA
+//   hk   : H[k][col] = sum_l c[l][col] W^{k d_l}  (1024 bins x 15 sparse taps x 16 complex columns per frame: the
+//          per-subcarrier channel matrices of the 2x2 headline, 4 coefficient sets) — FFMA2 residue-class form of
+//          ofdm_tdl_pair.cuh against a 3xTF32 mma.sync GEMM whose A fragments are gathered from the twiddle table
+//   fir  : the time-varying sparse FIR of the 2x2 headline (quadratic tap polynomial) — FFMA2 form of
+//          ofdm_tdl_pair.cuh against C[16, N] = A[16, 64] X_toeplitz[64, N] with 3xTF32 mma.sync
+//   gram : 4x4 complex H^H H + s2 I and H^H y per subcarrier (C5) — per-thread DFMA against FP64 DMMA m8n8k4 on the
+//          real 8x8 embedding, fragments staged through shared memory
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+#include <cuda_runtime.h>
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); return 1; } } while (0)
+
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pk2(float a, float b) { return (u64)__float_as_uint(a) | ((u64)__float_as_uint(b) << 32); }
+__device__ __forceinline__ void upk2(u64 v, float &a, float &b) { a = __uint_as_float((unsigned)v); b = __uint_as_float((unsigned)(v >> 32)); }
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ u64 sub2(u64 a, u64 b) { return fma2(b, pk2(-1.f, -1.f), a); }
+
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__device__ __forceinline__ void mma_f16(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__device__ __forceinline__ void mma_f64(double (&d)[2], double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d[0]), "+d"(d[1]) : "d"(a), "d"(b));
+}
+// x = hi + lo with hi representable in tf32 (the mma reads only the upper 19 bits of lo)
+__device__ __forceinline__ void split_tf32(float x, uint32_t &hi, uint32_t &lo) {
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+    lo = __float_as_uint(x - __uint_as_float(hi));
+}
+
+static int g_sms = 148;
+template <typename F> static float time_ms(F launch, int reps = 5) {
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    launch(); launch();
+    cudaDeviceSynchronize();
+    float best = 1e30f;
+    for (int r = 0; r < reps; ++r) {
+        cudaEventRecord(e0); launch(); cudaEventRecord(e1); cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        if (ms < best) best = ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return best;
+}
+
+// ------------------------------------------------------------------------------------------------ raw rates
+template <int MODE> __global__ void __launch_bounds__(256) raw_kernel(float *out, int iters) {
+    const int lane = threadIdx.x & 31;
+    float r = 0.f;
+    if (MODE == 0) {                   // tf32 m16n8k8
+        float d[8][4] = {};
+        uint32_t a[4] = {__float_as_uint(1.0f + lane), __float_as_uint(0.5f), __float_as_uint(0.25f), __float_as_uint(2.f)};
+        uint32_t b[2] = {__float_as_uint(0.001f * lane), __float_as_uint(0.002f)};
+        for (int it = 0; it < iters; ++it)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) mma_tf32(d[i], a, b);
+        for (int i = 0; i < 8; ++i) r += d[i][0] + d[i][1] + d[i][2] + d[i][3];
+    } else if (MODE == 1) {            // f16 m16n8k16
+        float d[8][4] = {};
+        uint32_t a[4] = {0x3c003c00u + lane, 0x38003800u, 0x34003400u, 0x3c003800u};
+        uint32_t b[2] = {0x2c002c00u + lane, 0x28002800u};
+        for (int it = 0; it < iters; ++it)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) mma_f16(d[i], a, b);
+        for (int i = 0; i < 8; ++i) r += d[i][0] + d[i][1] + d[i][2] + d[i][3];
+    } else if (MODE == 2) {            // f64 m8n8k4
+        double d[8][2] = {};
+        const double a = 1.0 + lane * 1e-3, b = 0.5 - lane * 1e-3;
+        for (int it = 0; it < iters; ++it)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) mma_f64(d[i], a, b);
+        for (int i = 0; i < 8; ++i) r += float(d[i][0] + d[i][1]);
+    } else if (MODE == 3) {            // FFMA2
+        u64 d[8];
+        for (int i = 0; i < 8; ++i) d[i] = pk2(lane * 0.001f + i, i * 0.5f);
+        const u64 b = pk2(0.999f, 0.9995f), c = pk2(0.25f, 0.125f);
+        for (int it = 0; it < iters; ++it)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) d[i] = fma2(d[i], b, c);
+        for (int i = 0; i < 8; ++i) { float x, y; upk2(d[i], x, y); r += x + y; }
+    } else {                           // DFMA
+        double d[8];
+        for (int i = 0; i < 8; ++i) d[i] = lane * 0.001 + i;
+        const double b = 0.999, c = 0.25;
+        for (int it = 0; it < iters; ++it)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) d[i] = fma(d[i], b, c);
+        for (int i = 0; i < 8; ++i) r += float(d[i]);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = r;
+}
+
+static int run_raw() {
+    float *out;
+    const int ctas = g_sms * 4, iters = 4000;
+    CK(cudaMalloc(&out, size_t(ctas) * 256 * 4));
+    const char *names[5] = {"mma.sync.m16n8k8.tf32", "mma.sync.m16n8k16.f16", "mma.sync.m8n8k4.f64", "fma.rn.f32x2", "fma.rn.f64"};
+    const double fma_per_warp_inst[5] = {16. * 8 * 8, 16. * 8 * 16, 8. * 8 * 4, 64., 32.};
+    for (int mode = 0; mode < 5; ++mode) {
+        auto launch = [&] {
+            switch (mode) {
+                case 0: raw_kernel<0><<<ctas, 256>>>(out, iters); break;
+                case 1: raw_kernel<1><<<ctas, 256>>>(out, iters); break;
+                case 2: raw_kernel<2><<<ctas, 256>>>(out, iters); break;
+                case 3: raw_kernel<3><<<ctas, 256>>>(out, iters); break;
+                default: raw_kernel<4><<<ctas, 256>>>(out, iters); break;
+            }
+        };
+        const float ms = time_ms(launch);
+        const double winst = double(ctas) * 8 * iters * 8;
+        printf("{\"experiment\": \"raw\", \"inst\": \"%s\", \"ms\": %.4f, \"warp_inst_per_s\": %.4g, \"warp_inst_per_clk_per_sm_at_1965MHz\": %.4f, \"tflops\": %.2f}\n",
+               names[mode], ms, winst / ms * 1e3, winst / ms * 1e3 / (g_sms * 1.965e9), 2 * winst * fma_per_warp_inst[mode] / ms / 1e9);
+    }
+    CK(cudaGetLastError());
+    cudaFree(out);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ H_k
+constexpr int kFft = 1024, kTaps = 15, kCols = 16;      // complex columns: 4 coefficient sets x (2 x 2) entries
+__constant__ int c_delay[16];
+
+// FFMA2 form (ofdm_tdl_pair.cuh tap_sum): a thread owns bins k0 + u fft/4, taps summed per delay class mod 4 and the
+// class sums combined by a 4-point DFT; columns in packed pairs (2 complex columns per ps), one set of 4 columns per pass
+struct ps { u64 re, im; };
+__global__ void __launch_bounds__(256, 3) hk_ffma2_kernel(const float2 *__restrict__ coef, float2 *__restrict__ out, float *chk,
+                                                          int n_frames, const int *cls_start, const int *cls_delay, const int *cls_tap) {
+    __shared__ float2 tw[kFft];
+    __shared__ float4 gb[kTaps * kCols / 2];               // [sorted tap][col pair] = (a.re, b.re, a.im, b.im)
+    __shared__ int s_start[5], s_delay[16];
+    const int tid = threadIdx.x;
+    for (int i = tid; i < kFft; i += 256) { float s, c; sincospif(-2.0f * i / kFft, &s, &c); tw[i] = make_float2(c, s); }
+    if (tid < 5) s_start[tid] = cls_start[tid];
+    if (tid < kTaps) s_delay[tid] = cls_delay[tid];
+    float acc = 0.f;
+    for (int f = blockIdx.x; f < n_frames; f += gridDim.x) {
+        __syncthreads();
+        for (int i = tid; i < kTaps * kCols / 2; i += 256) {
+            const int j = i / (kCols / 2), cp = i % (kCols / 2);
+            const float2 a = coef[(size_t(f) * kTaps + cls_tap[j]) * kCols + 2 * cp], b = coef[(size_t(f) * kTaps + cls_tap[j]) * kCols + 2 * cp + 1];
+            gb[i] = make_float4(a.x, b.x, a.y, b.y);
+        }
+        __syncthreads();
+        const int k0 = tid;
+#pragma unroll 1
+        for (int set = 0; set < kCols / 4; ++set) {
+            ps Hc[4][2];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) for (int q = 0; q < 2; ++q) Hc[u][q] = {0ull, 0ull};
+            auto tap_sum = [&](ps (&a)[2], int j0, int j1) {
+                for (int j = j0; j < j1; ++j) {
+                    const float2 w = tw[(k0 * s_delay[j]) & (kFft - 1)];
+                    const u64 WR = pk2(w.x, w.x), WI = pk2(w.y, w.y), NWI = pk2(-w.y, -w.y);
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        const float4 g = gb[j * (kCols / 2) + set * 2 + q];
+                        const u64 gre = pk2(g.x, g.y), gim = pk2(g.z, g.w);
+                        a[q].re = fma2(gim, NWI, fma2(gre, WR, a[q].re));
+                        a[q].im = fma2(gim, WR, fma2(gre, WI, a[q].im));
+                    }
+                }
+            };
+            tap_sum(Hc[0], s_start[0], s_start[1]);
+            tap_sum(Hc[2], s_start[1], s_start[2]);
+            tap_sum(Hc[1], s_start[2], s_start[3]);
+            tap_sum(Hc[3], s_start[3], s_start[4]);
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const ps a0 = {add2(Hc[0][q].re, Hc[2][q].re), add2(Hc[0][q].im, Hc[2][q].im)};
+                const ps a1 = {sub2(Hc[0][q].re, Hc[2][q].re), sub2(Hc[0][q].im, Hc[2][q].im)};
+                const ps a2 = {add2(Hc[1][q].re, Hc[3][q].re), add2(Hc[1][q].im, Hc[3][q].im)};
+                const ps a3 = {sub2(Hc[1][q].re, Hc[3][q].re), sub2(Hc[1][q].im, Hc[3][q].im)};
+                ps y[4];
+                y[0] = {add2(a0.re, a2.re), add2(a0.im, a2.im)};
+                y[1] = {add2(a1.re, a3.im), sub2(a1.im, a3.re)};
+                y[2] = {sub2(a0.re, a2.re), sub2(a0.im, a2.im)};
+                y[3] = {sub2(a1.re, a3.im), add2(a1.im, a3.re)};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    float ar, br, ai, bi;
+                    upk2(y[u].re, ar, br); upk2(y[u].im, ai, bi);
+                    if (f == 0) {
+                        out[(k0 + u * 256) * kCols + set * 4 + 2 * q] = make_float2(ar, ai);
+                        out[(k0 + u * 256) * kCols + set * 4 + 2 * q + 1] = make_float2(br, bi);
+                    }
+                    acc += ar + br + ai + bi;
+                }
+            }
+        }
+    }
+    chk[blockIdx.x * 256 + tid] = acc;
+}
+
+// 3xTF32 mma.sync form.  Real GEMM C[1024, 32] = A[1024, 32] B[32, 32] per frame:
+//   A[k][(l, wr|wi)] = Re|Im W^{k d_l}, gathered from the twiddle table (one 8-byte load gives columns c and c + 4 of a
+//   k-step: taps 4 s + c);  B[(l, wr)][(j, re|im)] = (c_re, c_im), B[(l, wi)][(j, re|im)] = (-c_im, c_re), pre-split into
+//   tf32 hi / lo parts in fragment order in shared memory once per frame (one 16-byte load per k-step and column tile).
+// A warp owns pairs of 16-bin tiles; accumulators: 2 m-tiles x 4 n-tiles x 4 = 32 registers.
+template <int NPROD>
+__global__ void __launch_bounds__(256, 3) hk_mma_kernel(const float2 *__restrict__ coef, float2 *__restrict__ out, float *chk, int n_frames) {
+    __shared__ float2 tw[kFft];
+    __shared__ uint4 bfrag[4 * 4 * 32];                    // [k-step][n-tile][lane] = (b0.hi, b1.hi, b0.lo, b1.lo)
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, c = lane & 3;
+    for (int i = tid; i < kFft; i += 256) { float s, cs; sincospif(-2.0f * i / kFft, &s, &cs); tw[i] = make_float2(cs, s); }
+    float acc = 0.f;
+    for (int f = blockIdx.x; f < n_frames; f += gridDim.x) {
+        __syncthreads();
+        for (int i = tid; i < 4 * 4 * 32; i += 256) {
+            const int ln = i & 31, nt = (i >> 5) & 3, s = i >> 7;
+            const int gg = ln >> 2, cc = ln & 3, l = 4 * s + cc, j = 4 * nt + (gg >> 1), part = gg & 1;
+            float2 v = make_float2(0.f, 0.f);
+            if (l < kTaps) v = coef[(size_t(f) * kTaps + l) * kCols + j];
+            const float b0 = part ? v.y : v.x, b1 = part ? v.x : -v.y;
+            uint4 o;
+            split_tf32(b0, o.x, o.z);
+            split_tf32(b1, o.y, o.w);
+            bfrag[i] = o;
+        }
+        __syncthreads();
+#pragma unroll 1
+        for (int mp = warp; mp < kFft / 32; mp += 8) {
+            float d[2][4][4] = {};
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                uint32_t ahi[2][4], alo[2][4];
+                const int dl = c_delay[4 * s + c];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int k = mp * 32 + h * 16 + g;
+                    float2 w0 = tw[(k * dl) & (kFft - 1)], w1 = tw[((k + 8) * dl) & (kFft - 1)];
+                    if (4 * s + c >= kTaps) { w0 = make_float2(0.f, 0.f); w1 = w0; }
+                    split_tf32(w0.x, ahi[h][0], alo[h][0]);
+                    split_tf32(w1.x, ahi[h][1], alo[h][1]);
+                    split_tf32(w0.y, ahi[h][2], alo[h][2]);
+                    split_tf32(w1.y, ahi[h][3], alo[h][3]);
+                }
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) {
+                    const uint4 b = bfrag[(s * 4 + nt) * 32 + lane];
+                    const uint32_t bhi[2] = {b.x, b.y}, blo[2] = {b.z, b.w};
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        if (NPROD >= 3) mma_tf32(d[h][nt], alo[h], bhi);
+                        if (NPROD >= 2) mma_tf32(d[h][nt], ahi[h], blo);
+                        mma_tf32(d[h][nt], ahi[h], bhi);
+                    }
+                }
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) {
+                    if (f == 0) {
+                        const int k = mp * 32 + h * 16 + g;
+                        out[k * kCols + 4 * nt + c] = make_float2(d[h][nt][0], d[h][nt][1]);
+                        out[(k + 8) * kCols + 4 * nt + c] = make_float2(d[h][nt][2], d[h][nt][3]);
+                    }
+                    acc += d[h][nt][0] + d[h][nt][1] + d[h][nt][2] + d[h][nt][3];
+                }
+        }
+    }
+    chk[blockIdx.x * 256 + tid] = acc;
+}
+
+static const int h_delay[16] = {0, 3, 8, 10, 13, 19, 20, 21, 23, 25, 28, 29, 30, 31, 33, 0};
+
+static int run_hk() {
+    const int n_frames = g_sms * 3 * 24;
+    std::vector<float2> coef(size_t(n_frames) * kTaps * kCols);
+    uint32_t st = 12345u;
+    auto rnd = [&] { st = st * 1664525u + 1013904223u; return float(int32_t(st)) * (1.0f / 2147483648.0f); };
+    for (auto &v : coef) v = make_float2(rnd(), rnd());
+    // class-sorted tap order 0, 2, 1, 3 (mod 4), as the host does for ofdm_tdl_pair.cuh
+    int cls_start[5], cls_delay[16] = {}, cls_tap[16] = {}, n = 0;
+    const int order[4] = {0, 2, 1, 3};
+    for (int q = 0; q < 4; ++q) {
+        cls_start[q] = n;
+        for (int l = 0; l < kTaps; ++l) if ((h_delay[l] & 3) == order[q]) { cls_delay[n] = h_delay[l]; cls_tap[n] = l; ++n; }
+    }
+    cls_start[4] = n;
+    // double reference for frame 0
+    std::vector<double> ref(size_t(kFft) * kCols * 2, 0.0);
+    double ref_rms = 0;
+    for (int k = 0; k < kFft; ++k)
+        for (int j = 0; j < kCols; ++j) {
+            double re = 0, im = 0;
+            for (int l = 0; l < kTaps; ++l) {
+                const double a = -2.0 * M_PI * double((k * h_delay[l]) % kFft) / kFft, wr = cos(a), wi = sin(a);
+                const float2 cc = coef[size_t(l) * kCols + j];
+                re += cc.x * wr - cc.y * wi;
+                im += cc.x * wi + cc.y * wr;
+            }
+            ref[(size_t(k) * kCols + j) * 2] = re; ref[(size_t(k) * kCols + j) * 2 + 1] = im;
+            ref_rms += re * re + im * im;
+        }
+    ref_rms = sqrt(ref_rms / (kFft * kCols));
+    float2 *d_coef, *d_out; float *d_chk; int *d_cs, *d_cd, *d_ct;
+    CK(cudaMalloc(&d_coef, coef.size() * sizeof(float2)));
+    CK(cudaMemcpy(d_coef, coef.data(), coef.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&d_out, size_t(kFft) * kCols * sizeof(float2)));
+    CK(cudaMalloc(&d_chk, size_t(g_sms) * 3 * 256 * 4));
+    CK(cudaMalloc(&d_cs, 5 * 4)); CK(cudaMalloc(&d_cd, 16 * 4)); CK(cudaMalloc(&d_ct, 16 * 4));
+    CK(cudaMemcpy(d_cs, cls_start, 5 * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_cd, cls_delay, 16 * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_ct, cls_tap, 16 * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpyToSymbol(c_delay, h_delay, sizeof(h_delay)));
+    std::vector<float2> got(size_t(kFft) * kCols);
+    auto err = [&] {
+        cudaMemcpy(got.data(), d_out, got.size() * sizeof(float2), cudaMemcpyDeviceToHost);
+        double m = 0;
+        for (size_t i = 0; i < got.size(); ++i) {
+            m = fmax(m, fabs(got[i].x - ref[2 * i]));
+            m = fmax(m, fabs(got[i].y - ref[2 * i + 1]));
+        }
+        return m / ref_rms;
+    };
+    const int grid = g_sms * 3;
+    const char *names[4] = {"ffma2_residue_class", "mma_tf32_x3", "mma_tf32_x2", "mma_tf32_x1"};
+    for (int v = 0; v < 4; ++v) {
+        CK(cudaMemset(d_out, 0, got.size() * sizeof(float2)));
+        auto launch = [&] {
+            switch (v) {
+                case 0: hk_ffma2_kernel<<<grid, 256>>>(d_coef, d_out, d_chk, n_frames, d_cs, d_cd, d_ct); break;
+                case 1: hk_mma_kernel<3><<<grid, 256>>>(d_coef, d_out, d_chk, n_frames); break;
+                case 2: hk_mma_kernel<2><<<grid, 256>>>(d_coef, d_out, d_chk, n_frames); break;
+                default: hk_mma_kernel<1><<<grid, 256>>>(d_coef, d_out, d_chk, n_frames); break;
+            }
+        };
+        const float ms = time_ms(launch);
+        CK(cudaGetLastError());
+        printf("{\"experiment\": \"hk\", \"variant\": \"%s\", \"frames\": %d, \"ms\": %.4f, \"frames_per_s\": %.4g, \"us_sm_per_frame\": %.3f, "
+               "\"max_err_over_rms_vs_f64\": %.3g}\n", names[v], n_frames, ms, n_frames / ms * 1e3, ms * 1e3 * g_sms / n_frames, err());
+    }
+    cudaFree(d_coef); cudaFree(d_out); cudaFree(d_chk); cudaFree(d_cs); cudaFree(d_cd); cudaFree(d_ct);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ FIR
+// y_r[n] = sum_{l, t} (c0 + c1 tau + c2 tau^2)[l][r][t] x_t[n - d_l],  tau = n - (fft - 1) / 2, n in [0, fft), x has
+// kMem samples of history (cyclic prefix).  2 rx, 2 tx, 15 taps.
+constexpr int kMem = 40;
+
+// FFMA2 form: pair samples float4 (t0.re, t1.re, t0.im, t1.im), rx pair in the packed lanes, thread owns n = tid + jb 256
+__global__ void __launch_bounds__(256, 3) fir_ffma2_kernel(const float4 *__restrict__ x_g, const float2 *__restrict__ coef_g,
+                                                           float4 *__restrict__ out, float *chk, int n_frames) {
+    __shared__ float4 xs[kMem + kFft];
+    __shared__ ulonglong2 coef[kTaps * 2 * 3];              // [tap][t][order] = ((r0, r1).re, (r0, r1).im)
+    const int tid = threadIdx.x;
+    float acc = 0.f;
+    for (int f = blockIdx.x; f < n_frames; f += gridDim.x) {
+        __syncthreads();
+        for (int i = tid; i < kMem + kFft; i += 256) xs[i] = x_g[size_t(f) * (kMem + kFft) + i];
+        for (int i = tid; i < kTaps * 2 * 3; i += 256) {
+            const int l = i / 6, t = (i / 3) & 1, o = i % 3;
+            // coef_g[frame][l][o][r][t]
+            const float2 a = coef_g[(((size_t(f) * kTaps + l) * 3 + o) * 2 + 0) * 2 + t], b = coef_g[(((size_t(f) * kTaps + l) * 3 + o) * 2 + 1) * 2 + t];
+            coef[i] = make_ulonglong2(pk2(a.x, b.x), pk2(a.y, b.y));
+        }
+        __syncthreads();
+        u64 aRe[4] = {0, 0, 0, 0}, aIm[4] = {0, 0, 0, 0};
+        float tauv[4];
+#pragma unroll
+        for (int jb = 0; jb < 4; ++jb) tauv[jb] = float(tid + jb * 256) - 0.5f * (kFft - 1);
+        for (int l = 0; l < kTaps; ++l) {
+            const float4 *xl = xs + kMem + tid - c_delay[l];
+            float4 x4[4];
+#pragma unroll
+            for (int jb = 0; jb < 4; ++jb) x4[jb] = xl[jb * 256];
+#pragma unroll
+            for (int tt = 0; tt < 2; ++tt) {
+                u64 cR[3], cI[3];
+#pragma unroll
+                for (int o = 0; o < 3; ++o) { const ulonglong2 cc = coef[(l * 2 + tt) * 3 + o]; cR[o] = cc.x; cI[o] = cc.y; }
+#pragma unroll
+                for (int jb = 0; jb < 4; ++jb) {
+                    const u64 t2 = pk2(tauv[jb], tauv[jb]);
+                    const float xr = tt ? x4[jb].y : x4[jb].x, xi = tt ? x4[jb].w : x4[jb].z;
+                    const u64 xrr = pk2(xr, xr), xii = pk2(xi, xi), nxii = pk2(-xi, -xi);
+                    const u64 gR = fma2(fma2(cR[2], t2, cR[1]), t2, cR[0]), gI = fma2(fma2(cI[2], t2, cI[1]), t2, cI[0]);
+                    aRe[jb] = fma2(gI, nxii, fma2(gR, xrr, aRe[jb]));
+                    aIm[jb] = fma2(gI, xrr, fma2(gR, xii, aIm[jb]));
+                }
+            }
+        }
+#pragma unroll
+        for (int jb = 0; jb < 4; ++jb) {
+            float a, b, c, d;
+            upk2(aRe[jb], a, b); upk2(aIm[jb], c, d);
+            if (f == 0) out[tid + jb * 256] = make_float4(a, b, c, d);
+            acc += a + b + c + d;
+        }
+    }
+    chk[blockIdx.x * 256 + tid] = acc;
+}
+
+// 3xTF32 mma.sync form: C[16, N] = A[16, 64] X[64, N] per frame.  Rows m = o * 4 + r * 2 + part (12 used), K index of
+// k-step s: column c -> item i = 4 s + c = (tap l = i / 2, tx t = i & 1), real part; column c + 4 -> imaginary part;
+// A[(o, r, re)][(i, re)] = c_re, [(o, r, re)][(i, im)] = -c_im, [(o, r, im)][(i, re)] = c_im, [(o, r, im)][(i, im)] = c_re.
+// The A fragments (tf32 hi / lo) of a frame live in shared memory in fragment order; a B fragment is one 8-byte load of
+// x_t[n - d_l] (+ hi / lo split).  A warp owns 8-sample tiles; epilogue y = C_0 + tau C_1 + tau^2 C_2 via one shuffle.
+template <int NPROD>
+__global__ void __launch_bounds__(256, 3) fir_mma_kernel(const float4 *__restrict__ x_g, const float2 *__restrict__ coef_g,
+                                                         float4 *__restrict__ out, float *chk, int n_frames) {
+    __shared__ float2 xs[2][kMem + kFft];
+    __shared__ uint4 afrag[8 * 2 * 32];                     // [k-step][hi|lo][lane]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, c = lane & 3;
+    float acc = 0.f;
+    for (int f = blockIdx.x; f < n_frames; f += gridDim.x) {
+        __syncthreads();
+        for (int i = tid; i < kMem + kFft; i += 256) {
+            const float4 v = x_g[size_t(f) * (kMem + kFft) + i];
+            xs[0][i] = make_float2(v.x, v.z);
+            xs[1][i] = make_float2(v.y, v.w);
+        }
+        for (int i = tid; i < 8 * 32; i += 256) {
+            const int ln = i & 31, s = i >> 5, gg = ln >> 2, cc = ln & 3, it = 4 * s + cc, l = it >> 1, t = it & 1;
+            float a[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int row = gg + (e & 1) * 8, kim = e >> 1;      // a0 (g, c) a1 (g + 8, c) a2 (g, c + 4) a3 (g + 8, c + 4)
+                float v = 0.f;
+                if (row < 12 && l < kTaps) {
+                    const int o = row >> 2, r = (row >> 1) & 1, part = row & 1;
+                    const float2 cf = coef_g[(((size_t(f) * kTaps + l) * 3 + o) * 2 + r) * 2 + t];
+                    v = part == 0 ? (kim ? -cf.y : cf.x) : (kim ? cf.x : cf.y);
+                }
+                a[e] = v;
+            }
+            uint4 hi, lo;
+            split_tf32(a[0], hi.x, lo.x); split_tf32(a[1], hi.y, lo.y); split_tf32(a[2], hi.z, lo.z); split_tf32(a[3], hi.w, lo.w);
+            afrag[(s * 2 + 0) * 32 + ln] = hi;
+            afrag[(s * 2 + 1) * 32 + ln] = lo;
+        }
+        __syncthreads();
+        // delays of this lane's items
+        int dl[8], tl[8];
+#pragma unroll
+        for (int s = 0; s < 8; ++s) { const int it = 4 * s + c; dl[s] = c_delay[(it >> 1) & 15]; tl[s] = it & 1; }
+#pragma unroll 1
+        for (int nt = warp; nt < kFft / 8; nt += 8) {
+            float d[4] = {0.f, 0.f, 0.f, 0.f};
+            const int n0 = nt * 8;
+#pragma unroll
+            for (int s = 0; s < 8; ++s) {
+                const float2 xv = xs[tl[s]][kMem + n0 + g - dl[s]];
+                uint32_t bhi[2], blo[2];
+                split_tf32(xv.x, bhi[0], blo[0]);
+                split_tf32(xv.y, bhi[1], blo[1]);
+                const uint4 h4 = afrag[(s * 2 + 0) * 32 + lane], l4 = afrag[(s * 2 + 1) * 32 + lane];
+                const uint32_t ahi[4] = {h4.x, h4.y, h4.z, h4.w}, alo[4] = {l4.x, l4.y, l4.z, l4.w};
+                if (NPROD >= 3) mma_tf32(d, alo, bhi);
+                if (NPROD >= 2) mma_tf32(d, ahi, blo);
+                mma_tf32(d, ahi, bhi);
+            }
+            // rows g (d0, d1) and g + 8 (d2, d3), samples n0 + 2 c, n0 + 2 c + 1.  g < 4: orders 0 and 2 of (r, part) = g;
+            // 4 <= g < 8: order 1 (rows g + 8 >= 12 unused) -> fetch from lane + 16
+            const float t0 = float(n0 + 2 * c) - 0.5f * (kFft - 1), t1 = t0 + 1.f;
+            const float o1a = __shfl_down_sync(0xffffffffu, d[0], 16), o1b = __shfl_down_sync(0xffffffffu, d[1], 16);
+            const float ya = fmaf(fmaf(d[2], t0, o1a), t0, d[0]), yb = fmaf(fmaf(d[3], t1, o1b), t1, d[1]);
+            if (g < 4) {
+                if (f == 0) {
+                    // out[n] = (r0.re, r1.re, r0.im, r1.im); g = r * 2 + part
+                    float *o = reinterpret_cast<float *>(out);
+                    const int slot = (g & 1) * 2 + (g >> 1);
+                    o[(n0 + 2 * c) * 4 + slot] = ya;
+                    o[(n0 + 2 * c + 1) * 4 + slot] = yb;
+                }
+                acc += ya + yb;
+            }
+        }
+    }
+    chk[blockIdx.x * 256 + tid] = acc;
+}
+
+static int run_fir() {
+    const int n_frames = g_sms * 3 * 24;
+    std::vector<float4> x(size_t(n_frames) * (kMem + kFft));
+    std::vector<float2> coef(size_t(n_frames) * kTaps * 3 * 4);
+    uint32_t st = 777u;
+    auto rnd = [&] { st = st * 1664525u + 1013904223u; return float(int32_t(st)) * (1.0f / 2147483648.0f); };
+    for (auto &v : x) v = make_float4(rnd(), rnd(), rnd(), rnd());
+    const float oscale[3] = {1.f, 4e-6f, 1.6e-11f};          // realistic magnitudes: |c1 tau| ~ 2e-3, |c2 tau^2| ~ 4e-6
+    for (size_t i = 0; i < coef.size(); ++i) { const int o = int((i / 4) % 3); coef[i] = make_float2(rnd() * oscale[o], rnd() * oscale[o]); }
+    std::vector<double> ref(size_t(kFft) * 4, 0.0);
+    double rms = 0;
+    for (int n = 0; n < kFft; ++n) {
+        const double tau = n - 0.5 * (kFft - 1);
+        for (int r = 0; r < 2; ++r) {
+            double re = 0, im = 0;
+            for (int l = 0; l < kTaps; ++l)
+                for (int t = 0; t < 2; ++t) {
+                    double gr = 0, gi = 0, tp = 1;
+                    for (int o = 0; o < 3; ++o) { const float2 cf = coef[((size_t(l) * 3 + o) * 2 + r) * 2 + t]; gr += cf.x * tp; gi += cf.y * tp; tp *= tau; }
+                    const float4 xv = x[kMem + n - h_delay[l]];
+                    const double xr = t ? xv.y : xv.x, xi = t ? xv.w : xv.z;
+                    re += gr * xr - gi * xi;
+                    im += gr * xi + gi * xr;
+                }
+            ref[size_t(n) * 4 + r] = re; ref[size_t(n) * 4 + 2 + r] = im;
+            rms += re * re + im * im;
+        }
+    }
+    rms = sqrt(rms / (kFft * 2));
+    float4 *d_x, *d_out; float2 *d_coef; float *d_chk;
+    CK(cudaMalloc(&d_x, x.size() * sizeof(float4)));
+    CK(cudaMemcpy(d_x, x.data(), x.size() * sizeof(float4), cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&d_coef, coef.size() * sizeof(float2)));
+    CK(cudaMemcpy(d_coef, coef.data(), coef.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&d_out, kFft * sizeof(float4)));
+    CK(cudaMalloc(&d_chk, size_t(g_sms) * 3 * 256 * 4));
+    CK(cudaMemcpyToSymbol(c_delay, h_delay, sizeof(h_delay)));
+    std::vector<float> got(size_t(kFft) * 4);
+    auto err = [&] {
+        cudaMemcpy(got.data(), d_out, got.size() * 4, cudaMemcpyDeviceToHost);
+        double m = 0;
+        for (size_t i = 0; i < got.size(); ++i) m = fmax(m, fabs(got[i] - ref[i]));
+        return m / rms;
+    };
+    const int grid = g_sms * 3;
+    const char *names[3] = {"ffma2_pair", "mma_tf32_x3", "mma_tf32_x1"};
+    for (int v = 0; v < 3; ++v) {
+        CK(cudaMemset(d_out, 0, kFft * sizeof(float4)));
+        auto launch = [&] {
+            switch (v) {
+                case 0: fir_ffma2_kernel<<<grid, 256>>>(d_x, d_coef, d_out, d_chk, n_frames); break;
+                case 1: fir_mma_kernel<3><<<grid, 256>>>(d_x, d_coef, d_out, d_chk, n_frames); break;
+                default: fir_mma_kernel<1><<<grid, 256>>>(d_x, d_coef, d_out, d_chk, n_frames); break;
+            }
+        };
+        const float ms = time_ms(launch);
+        CK(cudaGetLastError());
+        printf("{\"experiment\": \"fir\", \"variant\": \"%s\", \"frames\": %d, \"ms\": %.4f, \"frames_per_s\": %.4g, \"us_sm_per_frame\": %.3f, "
+               "\"max_err_over_rms_vs_f64\": %.3g}\n", names[v], n_frames, ms, n_frames / ms * 1e3, ms * 1e3 * g_sms / n_frames, err());
+    }
+    cudaFree(d_x); cudaFree(d_coef); cudaFree(d_out); cudaFree(d_chk);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ 4x4 Gram (C5)
+// per subcarrier: A = H^H H + s2 I (Hermitian 4x4) and b = H^H y.  H[r][t] complex float (as the H_k phase leaves it).
+// Output: the 10 upper-triangle entries of A and the 4 entries of b as doubles (what the Cholesky solve consumes).
+// Every repetition rescales H by (1 + rep 2^-20) so that no repetition can be hoisted.
+constexpr int kGramOut = 28;     // doubles: 4 diag + 6 x 2 off-diag + 4 x 2 b
+
+__global__ void __launch_bounds__(256) gram_dfma_kernel(const float2 *__restrict__ H_g, const float2 *__restrict__ y_g, double *out,
+                                                        float *chk, int n_bins, int reps) {
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+    double accum = 0;
+    for (int rep = 0; rep < reps; ++rep) {
+        const float sc = 1.0f + float(rep) * 0x1p-20f;
+        for (int b = tid; b < n_bins; b += gridDim.x * blockDim.x) {
+            float2 H[4][4], y[4];
+            const float4 *hp = reinterpret_cast<const float4 *>(H_g + size_t(b) * 16);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float4 v = __ldg(hp + i);
+                H[i >> 1][(i & 1) * 2] = make_float2(sc * v.x, sc * v.y);
+                H[i >> 1][(i & 1) * 2 + 1] = make_float2(sc * v.z, sc * v.w);
+            }
+            const float4 *yp = reinterpret_cast<const float4 *>(y_g + size_t(b) * 4);
+#pragma unroll
+            for (int i = 0; i < 2; ++i) { const float4 v = __ldg(yp + i); y[2 * i] = make_float2(v.x, v.y); y[2 * i + 1] = make_float2(v.z, v.w); }
+            double o[kGramOut];
+            int w = 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                double dg = 1e-3;
+#pragma unroll
+                for (int r = 0; r < 4; ++r) dg = fma(double(H[r][i].x), double(H[r][i].x), fma(double(H[r][i].y), double(H[r][i].y), dg));
+                o[w++] = dg;
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = i + 1; j < 4; ++j) {
+                    double re = 0, im = 0;
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {       // conj(H[r][i]) * H[r][j]
+                        const double ar = H[r][i].x, ai = H[r][i].y, br = H[r][j].x, bi = H[r][j].y;
+                        re = fma(ar, br, fma(ai, bi, re));
+                        im = fma(ar, bi, fma(-ai, br, im));
+                    }
+                    o[w++] = re; o[w++] = im;
+                }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                double re = 0, im = 0;
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const double ar = H[r][i].x, ai = H[r][i].y, br = y[r].x, bi = y[r].y;
+                    re = fma(ar, br, fma(ai, bi, re));
+                    im = fma(ar, bi, fma(-ai, br, im));
+                }
+                o[w++] = re; o[w++] = im;
+            }
+            double s = 0;
+#pragma unroll
+            for (int i = 0; i < kGramOut; ++i) s += o[i];
+            accum += s;
+            if (rep == 0 && b < 1024)
+#pragma unroll
+                for (int i = 0; i < kGramOut; ++i) out[size_t(b) * kGramOut + i] = o[i];
+        }
+    }
+    chk[tid] = float(accum);
+}
+
+// DMMA form: real embedding E = [[Hr, -Hi], [Hi, Hr]] (8 x 8); D = E^T [E[:, 0:4] | y_emb | 0 0 0] (8 x 8, K = 8: two
+// m8n8k4).  D[0:4][0:4] = Re A, D[4:8][0:4] = Im A, D[:, 4] = (Re b, Im b).  A warp does one subcarrier per DMMA pair;
+// operands are gathered from the float H in shared memory (as the H_k phase could leave it) and the result is
+// scattered back through shared memory so that one thread owns one subcarrier for the solve.  All fragment <-> record
+// index maps are per-lane constants computed once.
+__global__ void __launch_bounds__(256) gram_dmma_kernel(const float2 *__restrict__ H_g, const float2 *__restrict__ y_g, double *out,
+                                                        float *chk, int n_bins, int reps) {
+    extern __shared__ __align__(16) unsigned char gram_smem[];      // 102 KB: opt-in dynamic shared memory
+    typedef float2 (*HsT)[32][17];          // per warp: 32 subcarriers x (16 H + pad)
+    typedef float2 (*YsT)[32][5];
+    typedef double (*DsT)[32][kGramOut + 1];
+    DsT Ds = reinterpret_cast<DsT>(gram_smem);
+    HsT Hs = reinterpret_cast<HsT>(gram_smem + sizeof(double) * 8 * 32 * (kGramOut + 1));
+    YsT ys = reinterpret_cast<YsT>(gram_smem + sizeof(double) * 8 * 32 * (kGramOut + 1) + sizeof(float2) * 8 * 32 * 17);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, c = lane & 3;
+    const int gw = blockIdx.x * 8 + warp, nw = gridDim.x * 8;
+    // A operand of k-step ks (row m = g = (mp, mt), col k = (kp = ks, rr = c)) = E[k][m]:
+    //   kp == mp -> Hr[rr][mt];  kp = 0, mp = 1 -> -Hi[rr][mt];  kp = 1, mp = 0 -> +Hi[rr][mt]
+    const int mp = g >> 2, a_idx = c * 4 + (g & 3);
+    const bool a0_im = (mp == 1), a1_im = (mp == 0);        // which component step 0 / step 1 reads
+    const float a0_sg = (mp == 1) ? -1.f : 1.f;             // step 0: Hr (mp = 0) or -Hi (mp = 1); step 1: +Hi (mp = 0) or Hr (mp = 1)
+    // B operand (row k = (ks, c), col n = g): n < 4 -> E[k][(0, n)] = (ks ? Hi : Hr)[c][n];  n == 4 -> y_emb[k];  else 0
+    const int b_idx = c * 4 + (g & 3);
+    // D[g][2c + e] -> record slot (or -1)
+    int slot[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+        const int row = g & 3, imag = g >> 2, col = 2 * c + e;
+        int sl = -1;
+        if (col < 4) {
+            if (row == col) { if (!imag) sl = row; }
+            else if (row < col) sl = 4 + 2 * (row * 4 - row * (row + 1) / 2 + (col - row - 1)) + imag;
+        } else if (col == 4) sl = 16 + 2 * row + imag;
+        slot[e] = sl;
+    }
+    double accum = 0;
+    for (int rep = 0; rep < reps; ++rep) {
+        const float sc = 1.0f + float(rep) * 0x1p-20f;
+        for (int b0 = gw * 32; b0 < n_bins; b0 += nw * 32) {
+            // stage 32 subcarriers (coalesced), as the producer phase would
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int e = i * 32 + lane;
+                const float2 v = __ldg(H_g + size_t(b0) * 16 + e);
+                Hs[warp][e >> 4][e & 15] = make_float2(sc * v.x, sc * v.y);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { const int e = i * 32 + lane; ys[warp][e >> 2][e & 3] = __ldg(y_g + size_t(b0) * 4 + e); }
+            __syncwarp();
+#pragma unroll 4
+            for (int sb = 0; sb < 32; ++sb) {
+                double d[2] = {0.0, 0.0};
+                const float2 ha = Hs[warp][sb][a_idx];
+                float2 hb = make_float2(0.f, 0.f);
+                if (g < 4) hb = Hs[warp][sb][b_idx];
+                else if (g == 4) hb = ys[warp][sb][c];
+                mma_f64(d, double(a0_sg * (a0_im ? ha.y : ha.x)), double(hb.x));
+                mma_f64(d, double(a1_im ? ha.y : ha.x), double(hb.y));
+                if (slot[0] >= 0) Ds[warp][sb][slot[0]] = d[0] + (slot[0] < 4 ? 1e-3 : 0.0);
+                if (slot[1] >= 0) Ds[warp][sb][slot[1]] = d[1] + (slot[1] < 4 ? 1e-3 : 0.0);
+            }
+            __syncwarp();
+            double s = 0;
+#pragma unroll
+            for (int i = 0; i < kGramOut; ++i) s += Ds[warp][lane][i];
+            accum += s;
+            if (rep == 0 && b0 + lane < 1024)
+                for (int i = 0; i < kGramOut; ++i) out[size_t(b0 + lane) * kGramOut + i] = Ds[warp][lane][i];
+            __syncwarp();
+        }
+    }
+    chk[blockIdx.x * blockDim.x + threadIdx.x] = float(accum);
+}
+
+static int run_gram() {
+    const int n_bins = g_sms * 8 * 256 * 4, reps = 20;
+    std::vector<float2> H(size_t(n_bins) * 16), y(size_t(n_bins) * 4);
+    uint32_t st = 99u;
+    auto rnd = [&] { st = st * 1664525u + 1013904223u; return float(int32_t(st)) * (1.0f / 2147483648.0f); };
+    for (auto &v : H) v = make_float2(rnd(), rnd());
+    for (auto &v : y) v = make_float2(rnd(), rnd());
+    // host reference (double) for the first 1024 subcarriers
+    std::vector<double> ref(size_t(1024) * kGramOut);
+    for (int b = 0; b < 1024; ++b) {
+        const float2 *h = &H[size_t(b) * 16], *yy = &y[size_t(b) * 4];
+        int w = 0;
+        double *o = &ref[size_t(b) * kGramOut];
+        for (int i = 0; i < 4; ++i) { double dg = 1e-3; for (int r = 0; r < 4; ++r) dg += double(h[r * 4 + i].x) * h[r * 4 + i].x + double(h[r * 4 + i].y) * h[r * 4 + i].y; o[w++] = dg; }
+        for (int i = 0; i < 4; ++i) for (int j = i + 1; j < 4; ++j) {
+            double re = 0, im = 0;
+            for (int r = 0; r < 4; ++r) { const double ar = h[r * 4 + i].x, ai = h[r * 4 + i].y, br = h[r * 4 + j].x, bi = h[r * 4 + j].y; re += ar * br + ai * bi; im += ar * bi - ai * br; }
+            o[w++] = re; o[w++] = im;
+        }
+        for (int i = 0; i < 4; ++i) {
+            double re = 0, im = 0;
+            for (int r = 0; r < 4; ++r) { const double ar = h[r * 4 + i].x, ai = h[r * 4 + i].y, br = yy[r].x, bi = yy[r].y; re += ar * br + ai * bi; im += ar * bi - ai * br; }
+            o[w++] = re; o[w++] = im;
+        }
+    }
+    float2 *d_H, *d_y; double *d_out; float *d_chk;
+    CK(cudaMalloc(&d_H, H.size() * sizeof(float2))); CK(cudaMemcpy(d_H, H.data(), H.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&d_y, y.size() * sizeof(float2))); CK(cudaMemcpy(d_y, y.data(), y.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&d_out, size_t(1024) * kGramOut * 8));
+    CK(cudaMalloc(&d_chk, size_t(g_sms) * 8 * 256 * 4));
+    std::vector<double> got(size_t(1024) * kGramOut);
+    const int grid = g_sms * 8;
+    const int kGramSmem = int(sizeof(double) * 8 * 32 * (kGramOut + 1) + sizeof(float2) * 8 * 32 * 17 + sizeof(float2) * 8 * 32 * 5);
+    CK(cudaFuncSetAttribute(gram_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGramSmem));
+    for (int v = 0; v < 2; ++v) {
+        CK(cudaMemset(d_out, 0, got.size() * 8));
+        auto launch = [&] {
+            if (v == 0) gram_dfma_kernel<<<grid, 256>>>(d_H, d_y, d_out, d_chk, n_bins, reps);
+            else gram_dmma_kernel<<<grid, 256, kGramSmem>>>(d_H, d_y, d_out, d_chk, n_bins, reps);
+        };
+        const float ms = time_ms(launch, 3);
+        CK(cudaGetLastError());
+        CK(cudaMemcpy(got.data(), d_out, got.size() * 8, cudaMemcpyDeviceToHost));
+        double diff = 0;
+        for (size_t i = 0; i < got.size(); ++i) diff = fmax(diff, fabs(got[i] - ref[i]));
+        printf("{\"experiment\": \"gram4x4\", \"variant\": \"%s\", \"subcarriers\": %.4g, \"ms\": %.4f, \"subcarriers_per_s\": %.4g, \"max_abs_err_vs_host_f64\": %.3g}\n",
+               v ? "dmma_m8n8k4_smem_staged" : "dfma_per_thread", double(n_bins) * reps, ms, double(n_bins) * reps / ms * 1e3, diff);
+    }
+    cudaFree(d_H); cudaFree(d_y); cudaFree(d_out); cudaFree(d_chk);
+    return 0;
+}
+
+int main(int argc, char **argv) {
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, 0));
+    g_sms = prop.multiProcessorCount;
+    const char *what = argc > 1 ? argv[1] : "all";
+    const bool all = !strcmp(what, "all");
+    if (all || !strcmp(what, "raw")) if (run_raw()) return 1;
+    if (all || !strcmp(what, "hk")) if (run_hk()) return 1;
+    if (all || !strcmp(what, "fir")) if (run_fir()) return 1;
+    if (all || !strcmp(what, "gram")) if (run_gram()) return 1;
+    return 0;
+}
