@@ -167,6 +167,34 @@ template <int N> __device__ __forceinline__ void cp_async_wait() {
 }
 __device__ __forceinline__ bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+// TMA bulk copies (cp.async.bulk, SASS UBLKCP) global -> shared, completion counted in bytes on an mbarrier: one
+// elected thread arms the barrier with the byte count and issues the copies, every consumer polls the barrier's
+// phase parity.  Source, destination and size must be multiples of 16 bytes.
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return unsigned(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(void *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(void *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void *bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "B200_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra B200_DONE_%=;\n"
+        "bra B200_WAIT_%=;\n"
+        "B200_DONE_%=:\n"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *smem, const void *gmem, unsigned bytes, void *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem)),
+                 "l"(gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
 template <typename P, int N> __device__ __forceinline__ P pick(P const (&arr)[N], int r) {
     P v = arr[0];
 #pragma unroll

@@ -275,6 +275,7 @@ ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const cx
     cx<T> *tw = (cx<T> *)take(sizeof(cx<T>) * (fft + kTwc));
     float4 *E2 = (float4 *)take(sizeof(float4) * (mem + S));            // one tx pair: [tail | cp | body]
     float4 *body = E2 + mem + cp;
+    take(32);                                                           // TMA landing pad: a row that starts 8 B off lands 16 B early
     float4 *pool = (float4 *)take(sizeof(float4) * (NP + 1) * fft);     // rx pair buffers + 1 scratch
     float4 *gb2 = (float4 *)take(sizeof(float4) * p.n_taps * NT * NP);  // mean taps [class-sorted tap][t][rx pair]
     float4 *tails = (float4 *)take(p.n_sym > 1 ? sizeof(float4) * TP * mem : 0);
@@ -292,6 +293,12 @@ ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const cx
     fill_compact_twiddles(tw, fft);
     if (m.kind != B200PHY_MODEM_BPSK)
         for (int k = tid; k < m.M; k += KT) tab[k] = tab_g[k];
+    __shared__ __align__(8) unsigned long long mbar[2];      // [0] noise rows of a symbol, [1] phases of the next frame
+    if (tid == 0) {
+        mbar_init(&mbar[0], 1);
+        mbar_init(&mbar[1], 1);
+        fence_mbar_init();
+    }
     __syncthreads();
 
     unsigned sym_err = 0, bit_err = 0;
@@ -317,10 +324,23 @@ ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const cx
     // rx FFT stage 0 straight from the FIR accumulators (one rx pair, one tx pair, one output block per frame)
     constexpr bool kFuseRx0 = (NP == 1 && TP == 1 && kJBC == 4);
     const bool rx0_fused = kFuseRx0 && fft == KT * kJBC;
+    // TMA input pipeline (stream mode, the shapes whose FIR output leaves the landing zone alone): the two noise
+    // rows of a symbol are two bulk copies into the rx pair buffer (rows back to back, not interleaved), the phases
+    // of the next frame two more; one thread issues them, completion is counted on an mbarrier.
+    const bool tma = !FUSED && rx0_fused && mem >= 1 && p.n_sym == 1;
+    const bool tma_ph = tma && pf16;
+    unsigned par_noise = 0, par_phase = 0;
+    const cx<T> *nrow0 = nullptr, *nrow1 = nullptr;
     uint2 idx_pre[kPre];
     auto prefetch = [&](long long f) {
         const T *gp = phi_g + size_t(f) * p.P, *gq = psi_g + size_t(f) * p.P;
-        if (pf16) {
+        if (tma_ph) {
+            if (tid == 0) {
+                mbar_expect_tx(&mbar[1], 2u * unsigned(p.P) * sizeof(T));
+                bulk_g2s(ph_phi, gp, unsigned(p.P) * sizeof(T), &mbar[1]);
+                bulk_g2s(ph_psi, gq, unsigned(p.P) * sizeof(T), &mbar[1]);
+            }
+        } else if (pf16) {
             for (int i = tid; i < (p.P >> 2); i += KT) {
                 cp_async<16>(ph_phi + 4 * i, gp + 4 * i);
                 cp_async<16>(ph_psi + 4 * i, gq + 4 * i);
@@ -359,7 +379,8 @@ ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const cx
                                                                     phase_from_word<T>(b2.z), phase_from_word<T>(b2.w));
             }
         } else if (pf) {
-            cp_async_wait<0>();                      // prefetched during the previous frame (visible after the barrier below)
+            if (tma_ph) { mbar_wait(&mbar[1], par_phase); par_phase ^= 1u; }
+            else cp_async_wait<0>();                 // prefetched during the previous frame (visible after the barrier below)
 #pragma unroll
             for (int u = 0; u < kPre; ++u)
                 if (tid + u * KT < (p.n_data >> 3)) reinterpret_cast<uint2 *>(dsym)[tid + u * KT] = idx_pre[u];
@@ -431,6 +452,23 @@ ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const cx
                                 Yp[q][j + 1] = make_float4(c0.re, c1.re, c0.im, c1.im);
                             }
                         }
+                } else if (tma) {
+                    // rows (2 q, 2 q + 1) of this symbol as two bulk copies.  A row that starts 8 bytes off a 16-byte
+                    // boundary is copied from one element earlier; sizes are rounded up to 16 bytes (the extra element
+                    // is still inside the row: mem >= 1).  The zone starts 32 bytes before the pair buffer.
+                    const size_t rowlen = size_t(p.N + mem);
+                    const cx<T> *s0 = noise_g + (size_t(frame) * NR) * rowlen + m0, *s1 = s0 + rowlen;
+                    const int sh0 = int((reinterpret_cast<uintptr_t>(s0) >> 3) & 1), sh1 = int((reinterpret_cast<uintptr_t>(s1) >> 3) & 1);
+                    const int c0 = (fft + sh0 + 1) & ~1, c1 = (fft + sh1 + 1) & ~1;
+                    cx<T> *land = reinterpret_cast<cx<T> *>(Yp[0]) - 4;
+                    nrow0 = land + sh0;
+                    nrow1 = land + c0 + sh1;
+                    if (tid == 0) {
+                        fence_proxy_async();             // the zone was last written by ordinary stores (previous FFT)
+                        mbar_expect_tx(&mbar[0], unsigned(c0 + c1) * sizeof(cx<T>));
+                        bulk_g2s(land, s0 - sh0, unsigned(c0) * sizeof(cx<T>), &mbar[0]);
+                        bulk_g2s(land + c0, s1 - sh1, unsigned(c1) * sizeof(cx<T>), &mbar[0]);
+                    }
                 } else if (apipe) {
                     // raw noise of rx 2q / 2q+1 at sample j lands in the two halves of the float4 slot j of the pair
                     // buffer (n0.re, n0.im, n1.re, n1.im); the FIR epilogue turns each slot into pair layout in
@@ -610,7 +648,18 @@ ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const cx
                         };
                         if (p.porder == 3) taps(std::true_type{}); else taps(std::false_type{});
                         ps yv[kJBC][NP];
-                        if (!FUSED && apipe && tp == 0) {
+                        if (!FUSED && tma) {
+                            // the two rows have landed (byte count complete on the barrier): y = sigma * noise + FIR
+                            mbar_wait(&mbar[0], par_noise);
+                            par_noise ^= 1u;
+                            const u64 sg = pk2(sigma, sigma);
+#pragma unroll
+                            for (int jb = 0; jb < kJBC; ++jb) {
+                                const cx<T> n0 = nrow0[tid + jo0 + jb * KT], n1 = nrow1[tid + jo0 + jb * KT];
+                                yv[jb][0].re = add2(mul2(pk2(n0.re, n1.re), sg), aRe[jb][0]);
+                                yv[jb][0].im = add2(mul2(pk2(n0.im, n1.im), sg), aIm[jb][0]);
+                            }
+                        } else if (!FUSED && apipe && tp == 0) {
                             // the raw noise has landed in this thread's slots: y = sigma * noise + FIR, re-laid as pairs
                             if (TP == 1) cp_async_wait<1>(); else cp_async_wait<0>();
                             const u64 sg = pk2(sigma, sigma);
@@ -850,6 +899,7 @@ ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const cx
                     }
                 }
             }
+            if (tma) fence_proxy_async();        // this frame's ordinary stores before the next frame's bulk copies
             __syncthreads();
         }   // OFDM symbols
     }       // frames
@@ -866,7 +916,7 @@ inline size_t ofdm_tdl_pair_smem(const OfdmP &p, int M, int NR, int NT) {
     size_t s = 0;
     s += al(sizeof(cx<float>) * (p.fft + kTwc));
     s += al(sizeof(float4) * (p.mem + p.S));
-    s += al(sizeof(float4) * (NP + 1) * p.fft);
+    s += 32 + al(sizeof(float4) * (NP + 1) * p.fft);
     s += al(sizeof(float4) * p.n_taps * NT * NP);
     s += al(p.n_sym > 1 ? sizeof(float4) * TP * p.mem : 0);
     s += al(sizeof(u64) * p.n_taps * NP * 2 * 4 * 2);

@@ -560,7 +560,7 @@ static int run_fir() {
 // per subcarrier: A = H^H H + s2 I (Hermitian 4x4) and b = H^H y.  H[r][t] complex float (as the H_k phase leaves it).
 // Output: the 10 upper-triangle entries of A and the 4 entries of b as doubles (what the Cholesky solve consumes).
 // Every repetition rescales H by (1 + rep 2^-20) so that no repetition can be hoisted.
-constexpr int kGramOut = 28;     // doubles: 4 diag + 6 x 2 off-diag + 4 x 2 b
+constexpr int kGramOut = 24;     // doubles: 4 diag + 6 x 2 off-diag + 4 x 2 b
 
 __global__ void __launch_bounds__(256) gram_dfma_kernel(const float2 *__restrict__ H_g, const float2 *__restrict__ y_g, double *out,
                                                         float *chk, int n_bins, int reps) {
