@@ -35,6 +35,7 @@ ofdm_tdl_fpair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const c
     cx<T> *tw = (cx<T> *)take(sizeof(cx<T>) * (fft + kTwc));
     float4 *E2 = (float4 *)take(sizeof(float4) * (mem + S));            // [tail | cp | body], lanes = frames
     float4 *body = E2 + mem + cp;
+    take(32);                                                           // TMA landing pad (see ofdm_tdl_pair.cuh)
     float4 *pool = (float4 *)take(sizeof(float4) * 2 * fft);            // rx buffer + scratch
     u64 *gbar = (u64 *)take(sizeof(u64) * p.n_taps * 2);                // [tap][re|im], lanes = frames
     float4 *tails = (float4 *)take(p.n_sym > 1 ? sizeof(float4) * mem : 0);
@@ -52,6 +53,12 @@ ofdm_tdl_fpair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const c
     fill_compact_twiddles(tw, fft);
     if (m.kind != B200PHY_MODEM_BPSK)
         for (int k = tid; k < m.M; k += kOT) tab[k] = tab_g[k];
+    __shared__ __align__(8) unsigned long long mbar[2];      // [0] noise rows of a symbol, [1] phases of the next pair
+    if (tid == 0) {
+        mbar_init(&mbar[0], 1);
+        mbar_init(&mbar[1], 1);
+        fence_mbar_init();
+    }
     __syncthreads();
 
     unsigned sym_err = 0, bit_err = 0;
@@ -73,15 +80,27 @@ ofdm_tdl_fpair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const c
                     (reinterpret_cast<uintptr_t>(idx_g) & 7) == 0;
     const bool pf16 = pf && (p.P & 3) == 0 && aligned16(phi_g) && aligned16(psi_g);
     const bool apipe = !FUSED;
+    // TMA input pipeline (see ofdm_tdl_pair.cuh): the noise rows of the two frames as two bulk copies into the rx
+    // buffer, the phases of the next pair as four more; one thread issues, completion counted on an mbarrier
+    const bool tma = !FUSED && rx0_fused && mem >= 1 && p.n_sym == 1;
+    const bool tma_ph = tma && pf16;
+    unsigned par_noise = 0, par_phase = 0;
+    const cx<T> *nrow0 = nullptr, *nrow1 = nullptr;
     uint2 idx_pre = make_uint2(0u, 0u);
     auto prefetch = [&](long long f) {               // f = first frame of the pair
         const bool ghost = f + 1 >= n_units;         // odd tail: lane 1 re-reads frame f
+        if (tma_ph && tid == 0) mbar_expect_tx(&mbar[1], 4u * unsigned(p.P) * sizeof(T));
 #pragma unroll
         for (int ln = 0; ln < 2; ++ln) {
             const long long fl = (ln && !ghost) ? f + 1 : f;
             const T *gp = phi_g + size_t(fl) * p.P, *gq = psi_g + size_t(fl) * p.P;
             T *dp = ph_phi + ln * p.P4, *dq = ph_psi + ln * p.P4;
-            if (pf16) {
+            if (tma_ph) {
+                if (tid == 0) {
+                    bulk_g2s(dp, gp, unsigned(p.P) * sizeof(T), &mbar[1]);
+                    bulk_g2s(dq, gq, unsigned(p.P) * sizeof(T), &mbar[1]);
+                }
+            } else if (pf16) {
                 for (int i = tid; i < (p.P >> 2); i += kOT) {
                     cp_async<16>(dp + 4 * i, gp + 4 * i);
                     cp_async<16>(dq + 4 * i, gq + 4 * i);
@@ -127,7 +146,8 @@ ofdm_tdl_fpair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const c
                                                                                 phase_from_word<T>(b2.z), phase_from_word<T>(b2.w));
             }
         } else if (pf) {
-            cp_async_wait<0>();                      // prefetched during the previous pair
+            if (tma_ph) { mbar_wait(&mbar[1], par_phase); par_phase ^= 1u; }
+            else cp_async_wait<0>();                 // prefetched during the previous pair
             if (tid < (p.n_data >> 2)) reinterpret_cast<uint2 *>(dsym)[tid] = idx_pre;
         } else {
 #pragma unroll
@@ -179,6 +199,22 @@ ofdm_tdl_fpair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const c
                             const cx<T> c0 = sigma * cnormal<T>(b0.z, b0.w), c1 = sigma * cnormal<T>(b1.z, b1.w);
                             Y[j + 1] = make_float4(c0.re, c1.re, c0.im, c1.im);
                         }
+                    }
+                } else if (tma) {
+                    // the rows of frame A / frame B as two bulk copies, back to back from 32 bytes before the rx buffer
+                    // (a row that starts 8 bytes off a 16-byte boundary is copied from one element earlier)
+                    const size_t rowlen = size_t(p.N + mem);
+                    const cx<T> *s0 = noise_g + size_t(frame) * rowlen + m0, *s1 = noise_g + size_t(frameB) * rowlen + m0;
+                    const int sh0 = int((reinterpret_cast<uintptr_t>(s0) >> 3) & 1), sh1 = int((reinterpret_cast<uintptr_t>(s1) >> 3) & 1);
+                    const int c0 = (fft + sh0 + 1) & ~1, c1 = (fft + sh1 + 1) & ~1;
+                    cx<T> *land = reinterpret_cast<cx<T> *>(Y) - 4;
+                    nrow0 = land + sh0;
+                    nrow1 = land + c0 + sh1;
+                    if (tid == 0) {
+                        fence_proxy_async();
+                        mbar_expect_tx(&mbar[0], unsigned(c0 + c1) * sizeof(cx<T>));
+                        bulk_g2s(land, s0 - sh0, unsigned(c0) * sizeof(cx<T>), &mbar[0]);
+                        bulk_g2s(land + c0, s1 - sh1, unsigned(c1) * sizeof(cx<T>), &mbar[0]);
                     }
                 } else if (apipe) {
                     const size_t rowlen = size_t(p.N + mem);
@@ -328,7 +364,17 @@ ofdm_tdl_fpair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const c
                     };
                     if (o3) taps(std::true_type{}); else taps(std::false_type{});
                     ps yv[kJBC];
-                    if (!FUSED && apipe) {
+                    if (!FUSED && tma) {
+                        mbar_wait(&mbar[0], par_noise);      // both rows have landed
+                        par_noise ^= 1u;
+                        const u64 sg = pk2(sigma, sigma);
+#pragma unroll
+                        for (int jb = 0; jb < kJBC; ++jb) {
+                            const cx<T> n0 = nrow0[tid + jo0 + jb * kOT], n1 = nrow1[tid + jo0 + jb * kOT];
+                            yv[jb].re = add2(mul2(pk2(n0.re, n1.re), sg), sub2(aRR[jb], aII[jb]));
+                            yv[jb].im = add2(mul2(pk2(n0.im, n1.im), sg), add2(aRI[jb], aIR[jb]));
+                        }
+                    } else if (!FUSED && apipe) {
                         // this thread's raw noise slots have landed: y = sigma * noise + FIR, re-laid as pairs
                         cp_async_wait<1>();
                         const u64 sg = pk2(sigma, sigma);
@@ -439,6 +485,7 @@ ofdm_tdl_fpair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const c
                     }
                 }
             }
+            if (tma) fence_proxy_async();        // this pair's ordinary stores before the next pair's bulk copies
             __syncthreads();
         }   // OFDM symbols
     }       // frame pairs
@@ -454,7 +501,7 @@ inline size_t ofdm_tdl_fpair_smem(const OfdmP &p, int M) {
     size_t s = 0;
     s += al(sizeof(cx<float>) * (p.fft + kTwc));
     s += al(sizeof(float4) * (p.mem + p.S));
-    s += al(sizeof(float4) * 2 * p.fft);
+    s += 32 + al(sizeof(float4) * 2 * p.fft);
     s += al(sizeof(u64) * p.n_taps * 2);
     s += al(p.n_sym > 1 ? sizeof(float4) * p.mem : 0);
     s += al(sizeof(u64) * p.n_taps * 4 * 2);
