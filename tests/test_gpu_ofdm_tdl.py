@@ -276,6 +276,34 @@ def test_frame_pair_kernel_vs_generic_kernel(mod, M, fft, cp, nsym, n):
     run_stream_vs_oracle(cfg, pair, np.arange(500, 502), exact=False, rel=REL_F32)
 
 
+@pytest.mark.parametrize('ant', [(1, 1), (2, 2)])
+@pytest.mark.parametrize('shift', [0, 1])
+def test_tma_input_pipeline_any_row_alignment(ant, shift):
+    """Stream mode of the two float32 kernels whose noise rows and phases arrive by TMA bulk copies
+    (cp.async.bulk + mbarrier, ofdm_tdl_pair.cuh / ofdm_tdl_fpair.cuh): the rows of consecutive frames start
+    alternately 0 and 8 bytes off a 16-byte boundary (odd row length), and a sliced noise / phase tensor moves
+    everything by one more element — every combination must give the fused-mode result bit for bit."""
+    import torch
+    cfg, link = make_pair('qam', 64, 1024, 72, 1024, Nr=ant[0], Nt=ant[1], dtype='f32', snr_dB=24.0)
+    n, first = 9, 40
+    idx, phi, psi, noise = link.draw(first, n)
+    c_f, hat_f = link.run(n, first_unit=first, want_idx=True)
+
+    def shifted(t):
+        flat = torch.empty(t.numel() + 1, dtype=t.dtype, device=t.device)
+        flat[shift:shift + t.numel()] = t.reshape(-1)
+        return flat[shift:shift + t.numel()].view(t.shape)
+
+    c_s, hat_s = link.run(n, first_unit=first, draws=(idx, shifted(phi), shifted(psi), shifted(noise)), want_idx=True)
+    assert np.array_equal(c_s, c_f) and torch.equal(hat_s, hat_f)
+    # every frame on its own: each row parity in the first landing slot
+    acc = torch.zeros(4, dtype=torch.int64, device='cuda')
+    for u in range(n):
+        link.run(1, first_unit=first + u, draws=(idx[u:u + 1], phi[u:u + 1], psi[u:u + 1], shifted(noise)[u:u + 1]),
+                 counters=acc)
+    assert np.array_equal(_t(acc), c_f)
+
+
 @pytest.mark.parametrize('n,first', [(1, 0), (7, 0), (7, 3), (20, 11)])
 def test_frame_pair_kernel_is_invariant_to_batch_and_shard_boundaries(n, first):
     """a frame's decisions must not depend on which lane / pair / batch it ran in.  Odd batches, odd

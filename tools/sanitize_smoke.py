@@ -23,6 +23,7 @@ def ofdm(fft, cp, used, Nr, Nt, nsym, dtype, pair=True, jakes='auto', Fd=10.0):
 
 
 cases = [ofdm(1024, 72, 1024, 2, 2, 2, 'f32'), ofdm(1024, 72, 1024, 2, 2, 1, 'f32', pair=False),
+         ofdm(1024, 72, 1024, 2, 2, 1, 'f32'),          # headline shape: TMA bulk input pipeline in stream mode
          ofdm(1024, 72, 600, 1, 1, 2, 'f32'), ofdm(256, 18, 200, 2, 2, 2, 'f64'),
          ofdm(256, 18, 200, 2, 1, 1, 'f32', jakes='recurrence', Fd=500.0), ofdm(2048, 144, 2048, 4, 4, 1, 'f32'),
          ofdm(512, 36, 300, 4, 2, 1, 'f64'),
