@@ -45,11 +45,12 @@ static int launch_one(const OfdmP &p, const Modem &m, const void *table, uint64_
 }
 
 // threads per CTA of the pair kernel for the big shapes (Nr Nt > 4: one CTA per SM, limited by shared
-// memory).  512 threads = 16 warps per SM instead of 8, but at 128 registers per thread the 4x4 detection
-// spills (388 B): measured on C5 -4 % in stream mode, +5 % with the fused RNG -> 256 stays the default
-// (-DB200_PAIR_BIG_KT=512 builds the variant).
+// memory) when fft is a multiple of 2048.  512 threads = 16 warps per SM instead of 8 at 128 registers per thread
+// (the 4x4 detection spills ~100 B).  Measured on C5 (r02, same box, three alternating runs): stream mode +0.3 %,
+// fused RNG +5.8 % -> 512 is the default (-DB200_PAIR_BIG_KT=256 builds the 8-warp variant).  All 16 warps run
+// the same phase between barriers, which is why doubling the warps buys so little: see DESIGN.md 4.2.
 #ifndef B200_PAIR_BIG_KT
-#define B200_PAIR_BIG_KT 256
+#define B200_PAIR_BIG_KT 512
 #endif
 
 template <bool FUSED, int NR, int NT, bool QAMK, int KT, int LGF>
