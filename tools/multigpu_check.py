@@ -50,6 +50,15 @@ def main():
     f4, n4 = D.shard(20003, first_unit=1)
     siso.run(n4, first_unit=f4, counters=c4)
     D.allreduce_counters(c4)
+    # C5 shape: 4x4 MMSE over 2048-subcarrier OFDM / TDL, 256-QAM (the 512-thread antenna-pair kernel)
+    Ts5 = 1.0 / (15e3 * 2048)
+    prof5 = COST259_TUx.get_discretize_profile(Ts5)
+    c5link = links.OfdmTdlLink(QAM(256), 2048, 144, 2048, Nr=4, Nt=4, tap_powers_linear=prof5.tap_powers_linear,
+                               tap_delays=prof5.tap_delays, Fd=10.0, Ts=Ts5, L=20, noise_var=1e-3, seed=79)
+    c5 = torch.zeros(4, dtype=torch.int64, device='cuda')
+    f5, n5 = D.shard(4003, first_unit=9)
+    c5link.run(n5, first_unit=f5, counters=c5)
+    D.allreduce_counters(c5)
     # the Monte Carlo runner: every rank drives the same LinkSimulationRunner, results must agree with 1 GPU
     from pyphysim_b200.simulations import LinkSimulationRunner
 
@@ -66,6 +75,7 @@ def main():
         ref2 = links.link_alamouti(QPSK(), 0.1, 10 ** 7 + 3)
         ref3 = links.link_siso_flat(QAM(64), 0.03, 10 ** 7 + 1)
         ref4 = siso.run(20003, first_unit=1)
+        ref5 = c5link.run(4003, first_unit=9)
         ref_se = []
         for snr in (20.0, 25.0):
             link.set_noise_var(10 ** (-snr / 10))
@@ -73,7 +83,8 @@ def main():
         same = r_se == ref_se
         ok &= same
         print('runner    world=%d sharded=%s single=%s %s' % (world, r_se, ref_se, 'OK' if same else 'MISMATCH'))
-        for name, a, b in (('ofdm2x2', c, ref), ('alamouti', c2, ref2), ('siso', c3, ref3), ('ofdm_siso_f32_odd', c4, ref4)):
+        for name, a, b in (('ofdm2x2', c, ref), ('alamouti', c2, ref2), ('siso', c3, ref3), ('ofdm_siso_f32_odd', c4, ref4),
+                           ('c5_4x4', c5, ref5)):
             same = np.array_equal(a.cpu().numpy(), b)
             ok &= same
             print('%-9s world=%d sharded=%s single=%s %s' % (name, world, a.cpu().numpy().tolist(), list(b),
