@@ -600,6 +600,15 @@ def measure_workload(work, steps, warm, world, quick, sampler=None):
                         "source": "ncu smsp__inst_executed.sum, profiles/ncu_%s.json" % work.wname}
     else:
         out["roofline"]["traffic_note"] = why
+    capf, _ = ncu_capture_for(work.wname + '_fused', kernel_fused)
+    if capf:
+        sm_mhz = (sampler.summary().get("sm_mhz") if sampler is not None else None) or 1965.0
+        peak_wi = 148 * 4 * sm_mhz * 1e6
+        rate = R / (ms_fused * 1e-3)
+        out["fused_rng"]["issue"] = {
+            "warp_inst_per_unit": float(capf['warp_inst_per_unit']), "achieved_warp_inst_per_s": rate * capf['warp_inst_per_unit'],
+            "peak_warp_inst_per_s": peak_wi, "frac": rate * capf['warp_inst_per_unit'] / peak_wi,
+            "source": "ncu smsp__inst_executed.sum, profiles/ncu_%s_fused.json" % work.wname}
 
     if not quick:
         # ---- e2e: the Monte Carlo mode through the SimulationRunner and the host-buffer C entry points

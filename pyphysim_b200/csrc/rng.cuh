@@ -103,9 +103,35 @@ __device__ __forceinline__ void sincos2pi(float u, float *s, float *c) {
 }
 __device__ __forceinline__ void sincos2pi(double u, double *s, double *c) { sincospi(2.0 * u, s, c); }
 
+// sqrt(-ln u) for the Box-Muller radius.  u = (x + 0.5) 2^-32 rounded to float lies in [2^-33, 1]: positive, finite,
+// never subnormal, so the library routines' special-case handling (zero, negative, infinity, subnormal scaling: 5 of
+// logf's 22 instructions, and sqrtf's slow-path branch) is dead weight in a generator that runs twice per noise
+// sample.  Float: ln u = e ln 2 + log1p(m - 1) with m in [2/3, 4/3) (minimax polynomial, < 1 ulp), then
+// sqrt.approx (MUFU.SQRT, 1 ulp).  Double: the library routines.
+__device__ __forceinline__ float boxmuller_radius(float u) {
+    const int i = __float_as_int(u);
+    const int e = (i - 0x3f2aaaab) & int(0xff800000);          // exponent that puts the mantissa in [2/3, 4/3)
+    const float m = __int_as_float(i - e) - 1.0f, s = m * m;
+    float r = -0.130310059f, t = 0.140869141f;
+    r = fmaf(r, s, -0.121484190f);
+    t = fmaf(t, s, 0.139814854f);
+    r = fmaf(r, s, -0.166846052f);
+    t = fmaf(t, s, 0.200120345f);
+    r = fmaf(r, s, -0.249996200f);
+    r = fmaf(t, m, r);
+    r = fmaf(r, m, 0.333331972f);
+    r = fmaf(r, m, -0.5f);
+    r = fmaf(r, s, m);                                          // log1p(m)
+    const float nl = -fmaf(float(e), 8.26295829e-8f, r);       // -(e / 2^23) ln 2 - log1p(m): e is a multiple of 2^23
+    float rad;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad) : "f"(fmaxf(nl, 0.0f)));
+    return rad;
+}
+__device__ __forceinline__ double boxmuller_radius(double u) { return sqrt(-log(u)); }
+
 // complex normal with E|c|^2 = 1 (randn_c, util/misc.py:327-355) by Box-Muller on two words
 template <typename T> __device__ __forceinline__ cx<T> cnormal(uint32_t w0, uint32_t w1) {
-    const T rad = sqrt(-log(uniform01<T>(w0)));
+    const T rad = boxmuller_radius(uniform01<T>(w0));
     T s, c;
     sincos2pi(uniform01<T>(w1), &s, &c);
     return {rad * c, rad * s};

@@ -2,10 +2,17 @@
 """Per BAR-delimited region: share of executed instructions vs share of warp-stall samples (time)."""
 import csv, subprocess, sys
 rep = sys.argv[1]
-out = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv', '--print-source', 'sass'], capture_output=True, text=True).stdout
+which = sys.argv[2] if len(sys.argv) > 2 else '0'
+out = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv', '--print-source', 'sass', '--launch-skip', which, '--launch-count', '1'], capture_output=True, text=True).stdout
 rows = [r for r in csv.reader(out.splitlines())]
 hdr = next(r for r in rows if r and r[0] == 'Address')
-k = [r for r in rows if r and r[0].startswith('0x')]
+k = []
+seen_hdr = 0
+for r in rows:                                  # the page lists each kernel once per source view: keep the first listing
+    if r and r[0] == 'Address':
+        seen_hdr += 1
+    elif r and r[0].startswith('0x') and seen_hdr == 1:
+        k.append(r)
 i_ins, i_smp = hdr.index('Instructions Executed'), hdr.index('# Samples')
 stall_cols = [(i, h) for i, h in enumerate(hdr) if h.startswith('stall_') and 'Not Issued' not in h]
 ti = sum(int(r[i_ins]) for r in k); ts = sum(int(r[i_smp]) for r in k)

@@ -8,8 +8,8 @@ from collections import Counter
 
 rep = sys.argv[1]
 which = int(sys.argv[2]) if len(sys.argv) > 2 else 0
-out = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv', '--print-source', 'sass'],
-                     capture_output=True, text=True).stdout
+out = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv', '--print-source', 'sass', '--launch-skip', str(which),
+                      '--launch-count', '1'], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 kernels, cur = [], None
 for r in rows:
@@ -18,9 +18,10 @@ for r in rows:
         kernels.append(cur)
     elif cur is not None and r and r[0].startswith('0x'):
         cur.append(r)
-k = kernels[which]
+k = kernels[0]
+name = next((r[1] for r in rows if r and r[0] == 'Kernel Name'), '?').split('(b200phy')[0]
 total = sum(int(r[5]) for r in k)
-print('kernel %d: %d SASS instructions, %d executed warp-instructions' % (which, len(k), total))
+print('kernel %d %s: %d SASS instructions, %d executed warp-instructions' % (which, name, len(k), total))
 seg, ops, n0 = 0, Counter(), 0
 def flush(i, tag):
     global seg, ops, n0

@@ -2,7 +2,7 @@
 """profiles/ncu_<workload>.json from an `ncu --set full` capture: the per-unit instruction and DRAM figures bench.py
 quotes in `roofline.traffic` / `issue`, keyed by the kernel instantiation they were measured on.
 
-    python tools/ncu_to_json.py report.ncu-rep UNITS_PER_LAUNCH [kernel-regex] > profiles/ncu_<workload>.json
+    python tools/ncu_to_json.py report.ncu-rep UNITS_PER_LAUNCH [kernel-regex | #N] > profiles/ncu_<workload>.json
 
 bench.py compares the `kernel` field with b200phy_last_kernel() of its own launch and refuses a capture of a
 different instantiation, so a profile that went stale with a kernel change is never quoted."""
@@ -35,20 +35,21 @@ def normalise(name):
 
 def main():
     rep, units = sys.argv[1], int(sys.argv[2])
-    rx = re.compile(sys.argv[3]) if len(sys.argv) > 3 else None
+    sel = sys.argv[3] if len(sys.argv) > 3 else None          # kernel-name regex, or '#N' = N-th captured launch
+    rx = re.compile(sel) if sel and not sel.startswith('#') else None
     out = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr = rows[0]
     body = [r for r in rows[2:] if len(r) == len(hdr)]
     if rx:
         body = [r for r in body if rx.search(r[hdr.index('Kernel Name')])]
-    r = body[-1]
+    r = body[int(sel[1:])] if sel and sel.startswith('#') else body[-1]
 
     def g(metric):
         return float(r[hdr.index(metric)].replace(',', '')) if metric in hdr else None
 
     def to_bytes(metric):
-        v, u = g(metric), rows[1][hdr.index(metric)]
+        v, u = g(metric), rows[1][hdr.index(metric)].split('/')[0]
         return v * {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}.get(u, 1)
 
     dur, du = g('gpu__time_duration.sum'), rows[1][hdr.index('gpu__time_duration.sum')]
