@@ -158,14 +158,49 @@ def tu_profile(fft):
     return COST259_TUx.get_discretize_profile(Ts), Ts
 
 
-def make_link(w, dtype='f32'):
+def make_link(w, dtype='f32', tensor_cores=False):
     from pyphysim_b200 import links
     from pyphysim_b200.modulators import QAM
     prof, Ts = tu_profile(w['fft'])
     return links.OfdmTdlLink(QAM(w['M']), w['fft'], w['cp'], w['used'], num_ofdm_symbols=w['n_sym'],
                              Nr=w['Nr'], Nt=w['Nt'], tap_powers_linear=prof.tap_powers_linear,
                              tap_delays=prof.tap_delays, Fd=10.0, Ts=Ts, L=20,
-                             noise_var=1.0 / dB2Linear(w['snr_dB']), dtype=dtype, seed=SEED)
+                             noise_var=1.0 / dB2Linear(w['snr_dB']), dtype=dtype, seed=SEED,
+                             use_tensor_cores=tensor_cores)
+
+
+def measure_tensor_core_variant(w, R, steps, world, lib, base_value, base_fused):
+    """The same workload with the per-subcarrier channel matrices on the tensor cores (tcgen05, 3xTF32, opt-in): its
+    rates beside the default kernel's, its counters against the default kernel's on the same frames."""
+    import torch
+    link = make_link(w, tensor_cores=True)
+    first = 0
+    draws = link.draw(first, R)
+    cnt = torch.zeros(4, dtype=torch.int64, device='cuda')
+    stream = lambda: link.run(R, first_unit=first, draws=draws, counters=cnt)       # noqa: E731
+    fused = lambda: link.run(R, first_unit=first, counters=cnt)                     # noqa: E731
+    for _ in range(3):
+        stream()
+    ms_s = timed(stream, steps, world)
+    kernel = lib.b200phy_last_kernel().decode()
+    for _ in range(3):
+        fused()
+    ms_f = timed(fused, steps, world)
+    c_tc = link.run(R, first_unit=first, draws=draws)
+    c_cc = make_link(w).run(R, first_unit=first, draws=draws)
+    del draws
+    cap, _ = ncu_capture_for(DEFAULT + '_tcgen05', kernel)
+    out = {"kernel": kernel, "value": R / (ms_s * 1e-3), "fused_rng": R / (ms_f * 1e-3), "unit": UNIT,
+           "vs_default_stream": R / (ms_s * 1e-3) / base_value, "vs_default_fused": R / (ms_f * 1e-3) / base_fused,
+           "symbol_count_drift_vs_default": int(c_tc[0]) - int(c_cc[0]), "bit_count_drift_vs_default": int(c_tc[1]) - int(c_cc[1]),
+           "units": R, "adopted": False,
+           "what": "H_k = sum_j gbar_j W^(k d_j) of a frame as one tcgen05 tile (M 128 x N 64 x K 32, 3xTF32, DFT operand "
+                   "resident in TMEM, 12 MMAs per frame): fewer instructions, not faster (the kernel is bound by the FMA pipe "
+                   "of the FIR); opt-in via OfdmTdlLink(use_tensor_cores=True) / params.reserved bit 1"}
+    if cap:
+        out["tensor_pipe_pct"] = cap.get('tensor_pipe_pct')
+        out["warp_inst_per_unit"] = cap.get('warp_inst_per_unit')
+    return out
 
 
 def oracle_frame_runner(w):
@@ -710,6 +745,11 @@ def main():
                        "slowdown_vs_f32_fused": (world * work.R / (line["fused_rng"]["ms_per_step"] * 1e-3)) /
                                                 (world * R64 / (ms64 * 1e-3))}
     work.release()
+
+    if not args.quick and wname == DEFAULT and world == 1:
+        # ---- the tensor-core variant of the headline kernel (tcgen05 H_k, opt-in): measured beside the default
+        line["tensor_core_variant"] = measure_tensor_core_variant(w, min(work.R, 50000), max(3, args.steps // 2), world, lib,
+                                                                  line["value"], line["fused_rng"]["value"])
 
     if not (args.quick or args.no_configs) and wname == DEFAULT:
         cfgs = {}

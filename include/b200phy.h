@@ -89,7 +89,9 @@ typedef struct b200phy_ofdm_tdl_params {
     int32_t n_taps;       /* discretised profile (channels/fading.py:272-304) */
     int32_t L;            /* Jakes rays (channels/fading_generators.py:319-351) */
     int32_t jakes_mode;   /* B200PHY_JAKES_* */
-    int32_t reserved;     /* flags; bit 0 = do not use the antenna-pair FFMA2 kernel (A/B, tests) */
+    int32_t reserved;     /* flags; bit 0 = do not use the antenna-pair FFMA2 kernel (A/B, tests); bit 1 = compute the
+                             per-subcarrier channel matrices of the 2x2 / fft-1024 link on the tensor cores (tcgen05,
+                             3xTF32; measured 3 % slower than the CUDA-core form, hence opt-in) */
     int32_t delays[B200PHY_MAX_TAPS];    /* tap delays in samples, increasing */
     double tap_powers[B200PHY_MAX_TAPS]; /* linear tap powers */
     double Fd, Ts, t0;    /* Doppler [Hz], sample time [s], time of the frame's first sample */

@@ -107,6 +107,7 @@ static int fill_params(const b200phy_ofdm_tdl_params *q, const Modem &m, OfdmP *
     // float cos(phi) perturbs every ray frequency by ~1e-7 relative: harmless while the total phase
     // advance w0 * t_end stays small
     p.no_pair = (q->reserved & 1);
+    p.tc_hk = (q->reserved & 2) ? 1 : 0;
     p.cos_f32 = (q->dtype == B200PHY_F32) && (p.w0 * (fabs(q->t0) + p.N * p.Ts1) < 0.05);
     {
         const int items = q->n_taps * q->Nr;

@@ -40,6 +40,7 @@ struct OfdmP {
     int cos_f32;    // 1: cos(phi) may be evaluated in float (total phase advance is small)
     int cgrp;       // lanes cooperating on one (tap, rx) item in the oscillator setup (power of 2)
     int no_pair;    // 1: do not use the antenna-pair FFMA2 kernel (A/B and tests)
+    int tc_hk;      // 1: per-subcarrier channel matrices of the 2x2 / fft 1024 pair kernel through tcgen05 (3xTF32)
     int row;        // noise normals per rx row in the Philox layout: 2*ceil((N+mem)/2)
     int P, P4;      // phases per frame, rounded up to a multiple of 4
     int ifft_in_w;  // 1: scatter into W so that the ping-pong IFFT ends in E.body
@@ -190,6 +191,65 @@ __device__ __forceinline__ void mbar_wait(void *bar, unsigned parity) {
         "B200_DONE_%=:\n"
         "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+// ---- tcgen05 (5th-generation tensor cores): TMEM allocation, operand staging, MMA issue, read-back.
+// Shared-memory operand descriptor, K-major, no swizzle: 8-row x 16-byte core matrices; lbo = bytes between the two
+// 16-byte K chunks of one MMA, sbo = bytes between 8-row groups (cute::UMMA::SmemDescriptor, version 1).
+__device__ __forceinline__ unsigned long long umma_smem_desc(const void *p, unsigned lbo, unsigned sbo) {
+    return (unsigned long long)((smem_u32(p) >> 4) & 0x3fffu) | ((unsigned long long)((lbo >> 4) & 0x3fffu) << 16) |
+           ((unsigned long long)((sbo >> 4) & 0x3fffu) << 32) | (1ull << 46);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, dense, M x N
+__host__ __device__ constexpr unsigned umma_idesc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | (unsigned(N >> 3) << 17) | (unsigned(M >> 4) << 24);
+}
+// D[tmem] (+)= A[tmem] * B[smem]; issued by ONE thread
+__device__ __forceinline__ void umma_tf32_ts(unsigned d_tmem, unsigned a_tmem, unsigned long long b_desc, unsigned idesc,
+                                             unsigned accumulate) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void umma_commit(void *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(unsigned *smem_result, unsigned cols) {          // one full warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(unsigned addr, unsigned cols) {               // the same warp
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+// 32 consecutive 32-bit columns of this thread's TMEM lane (a warp reaches lanes 32 (warp % 4) .. + 31)
+__device__ __forceinline__ void tmem_st32(unsigned addr, const unsigned (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,"
+        "%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+        ::"r"(addr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+          "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]),
+          "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]),
+          "r"(v[30]), "r"(v[31]) : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_ld32(unsigned addr, unsigned (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,"
+        "%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(addr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// x = hi + lo, hi representable in tf32 (the MMA ignores the low 13 bits of lo)
+__device__ __forceinline__ void split_tf32(float x, unsigned &hi, unsigned &lo) {
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
+    lo = __float_as_uint(x - __uint_as_float(hi));
+}
+
 __device__ __forceinline__ void bulk_g2s(void *smem, const void *gmem, unsigned bytes, void *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem)),
                  "l"(gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");

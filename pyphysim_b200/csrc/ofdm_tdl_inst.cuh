@@ -53,11 +53,11 @@ static int launch_one(const OfdmP &p, const Modem &m, const void *table, uint64_
 #define B200_PAIR_BIG_KT 512
 #endif
 
-template <bool FUSED, int NR, int NT, bool QAMK, int KT, int LGF>
+template <bool FUSED, int NR, int NT, bool QAMK, int KT, int LGF, bool TC = false>
 static int launch_pair_kt(const OfdmP &p, const Modem &m, const void *table, uint64_t first_unit, int64_t n_units,
                           const uint8_t *idx, const void *phi, const void *psi, const void *noise,
                           uint8_t *idx_hat, void *eq_out, int64_t *counters, size_t smem, cudaStream_t st) {
-    auto kern = ofdm_tdl_pair_kernel<FUSED, NR, NT, QAMK, KT, LGF>;
+    auto kern = ofdm_tdl_pair_kernel<FUSED, NR, NT, QAMK, KT, LGF, TC>;
     int e = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)),
                        "cudaFuncSetAttribute(ofdm_tdl_pair_kernel)");
     if (e) return e;
@@ -68,13 +68,29 @@ static int launch_pair_kt(const OfdmP &p, const Modem &m, const void *table, uin
                    "cudaOccupancyMaxActiveBlocksPerMultiprocessor");
     if (e) return e;
     if (occ < 1) return -1;                       // does not fit: caller falls back to the generic kernel
+    if constexpr (TC) {
+        // This instantiation allocates tensor memory (tcgen05.alloc, 128 of the SM's 512 columns).  The occupancy API
+        // cannot know the column count and answers 1; the real limit is min(shared memory, registers, 512 / 128).
+        cudaFuncAttributes fa;
+        int smem_sm = 0, regs_sm = 0;
+        if (cudaFuncGetAttributes(&fa, kern) == cudaSuccess &&
+            cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev) == cudaSuccess &&
+            cudaDeviceGetAttribute(&regs_sm, cudaDevAttrMaxRegistersPerMultiprocessor, dev) == cudaSuccess) {
+            int o = int(size_t(smem_sm) / (smem + fa.sharedSizeBytes + 1024));
+            const int by_regs = regs_sm / (fa.numRegs * KT);
+            if (by_regs < o) o = by_regs;
+            if (o > 4) o = 4;
+            if (o > occ) occ = o;
+        }
+    }
     long long grid = (long long)sms * occ;
     if (grid > n_units) grid = n_units;
     kern<<<int(grid), KT, smem, st>>>(p, m, (const cx<float> *)table, first_unit, (long long)n_units, idx,
                                       (const float *)phi, (const float *)psi, (const cx<float> *)noise,
                                       idx_hat, (cx<float> *)eq_out, (unsigned long long *)counters);
     count_launch();
-    note_kernel("ofdm_tdl_pair_kernel<%d,%d,%d,%d,%d,%d>", int(FUSED), NR, NT, int(QAMK), KT, LGF);
+    if (TC) note_kernel("ofdm_tdl_pair_kernel<%d,%d,%d,%d,%d,%d,1>", int(FUSED), NR, NT, int(QAMK), KT, LGF);
+    else note_kernel("ofdm_tdl_pair_kernel<%d,%d,%d,%d,%d,%d>", int(FUSED), NR, NT, int(QAMK), KT, LGF);
     return check_cuda(cudaGetLastError(), "ofdm_tdl_pair_kernel launch");
 }
 
@@ -93,6 +109,11 @@ static int launch_pair_k(const OfdmP &p, const Modem &m, const void *table, uint
 #if B200_PAIR_STATIC_SHAPE
     // measured: +12 % on the 2x2 headline; the 4-antenna kernels (1 CTA/SM, 170-220 registers) get slower
     // with the fully unrolled FFT stages (C5 -12 %), so they keep the run-time shape
+    if constexpr (NR == 2 && NT == 2) {
+        // per-subcarrier channel matrices on the tensor cores (tcgen05, 3xTF32): see ofdm_tdl_pair.cuh
+        if (p.fft == 1024 && p.used == p.fft && ofdm_tdl_pair_tc_ok(p))
+            return launch_pair_kt<FUSED, NR, NT, QAMK, kOT, 10, true>(p, m, table, first_unit, n_units, idx, phi, psi, noise, idx_hat, eq_out, counters, smem, st);
+    }
     if constexpr (NR * NT <= 4) {
         if (p.fft == 1024 && p.used == p.fft)
             return launch_pair_kt<FUSED, NR, NT, QAMK, kOT, 10>(p, m, table, first_unit, n_units, idx, phi, psi, noise, idx_hat, eq_out, counters, smem, st);

@@ -253,7 +253,7 @@ __device__ __forceinline__ void ray_moments_f32(cx<float> (&a)[4], const float *
 // LGF: log2(fft) at compile time for the full-band shapes the BASELINE configs use (used == fft; 10 or 11),
 // 0 = run-time shape.  With the size known every FFT stage loop, stage-kind branch and bin -> position map
 // folds to constants (one trip per loop, immediate offsets).
-template <bool FUSED, int NR, int NT, bool QAMK, int KT = kOT, int LGF = 0>
+template <bool FUSED, int NR, int NT, bool QAMK, int KT = kOT, int LGF = 0, bool TC = false>
 __global__ void __launch_bounds__(KT, (NR * NT <= 4) ? 3 : 1)
 ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const cx<float> *__restrict__ tab_g,
                      uint64_t first_unit, long long n_units, const uint8_t *__restrict__ idx_g,
@@ -293,13 +293,60 @@ ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const cx
     fill_compact_twiddles(tw, fft);
     if (m.kind != B200PHY_MODEM_BPSK)
         for (int k = tid; k < m.M; k += KT) tab[k] = tab_g[k];
-    __shared__ __align__(8) unsigned long long mbar[2];      // [0] noise rows of a symbol, [1] phases of the next frame
+    __shared__ __align__(8) unsigned long long mbar[3];      // [0] noise rows of a symbol, [1] phases of the next frame, [2] H_k MMAs
+    __shared__ unsigned tmem_base_s;
     if (tid == 0) {
         mbar_init(&mbar[0], 1);
         mbar_init(&mbar[1], 1);
+        mbar_init(&mbar[2], 1);
         fence_mbar_init();
     }
+    // Tensor-core H_k (2x2, fft 1024, <= 16 taps, one OFDM symbol per frame): the per-subcarrier channel matrices
+    // H_k = sum_j gbar_j W^(k d_j) of a frame are ONE tcgen05 tile.  W^((k0 + off) d) = W^(k0 d) W^(off d) with
+    // off = 128 v + 256 u (8 offsets): all 1024 bins share the DFT operand of the bins k0 < 128, the coefficients are
+    // rotated by the 8th roots W^(off d) instead.  D[128, 64] = A[128, 32] B[32, 64]: A = (cos, sin) of W^(k0 d_j)
+    // (constant: tf32 hi / lo parts resident in TMEM, 64 columns), B = rotated coefficients (per frame, hi / lo, K-major
+    // in the tx sample buffer once the FIR has consumed it), D in TMEM (64 columns); 3xTF32 = 12 MMAs per frame issued
+    // by one thread, completion on mbar[2]; thread tid reads back exactly the bins tid + 256 u it detects.
+    // (template parameter TC; the launcher selects it: ofdm_tdl_pair_tc_ok)
+    static_assert(!TC || (LGF == 10 && NR == 2 && NT == 2 && KT == 256), "tensor-core H_k: 2x2, fft 1024, 256 threads");
+    constexpr bool kTcShape = TC;
+    constexpr bool tc = TC;
+    constexpr unsigned kTmemCols = 128;
+    if constexpr (kTcShape) {
+        if (tc && tid < 32) tmem_alloc(&tmem_base_s, kTmemCols);
+        if (tc) tc_fence_before();
+    }
     __syncthreads();
+    if constexpr (kTcShape) {
+        if (tc) tc_fence_after();
+    }
+    const unsigned tmem = tc ? tmem_base_s : 0u;
+    unsigned par_h = 0;
+    // B operand lives in the tx sample buffer (free between the FIR and the next frame's IFFT), 128-byte aligned;
+    // its descriptor is frame-invariant: K-major, no swizzle, 128 B between the K chunks, 256 B between 8-row groups
+    float *bop = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(E2) + 127) & ~uintptr_t(127));
+    const unsigned long long bdesc0 = umma_smem_desc(bop, 128, 256);
+    if constexpr (kTcShape) {
+        if (tc) {
+            if (tid < 128) {                                  // row k0 = tid of A: columns (2 j, 2 j + 1) = (cos, sin) of W^(k0 d_j)
+                unsigned hi[32], lo[32];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    cx<T> w = {0.f, 0.f};
+                    if (j < p.n_taps) w = tw[(tid * p.cls_delay[j]) & (fft - 1)];
+                    split_tf32(w.re, hi[2 * j], lo[2 * j]);
+                    split_tf32(w.im, hi[2 * j + 1], lo[2 * j + 1]);
+                }
+                const unsigned lane_base = unsigned(tid & ~31) << 16;
+                tmem_st32(tmem + lane_base, hi);
+                tmem_st32(tmem + 32 + lane_base, lo);
+            }
+            tc_fence_before();
+            __syncthreads();
+            tc_fence_after();
+        }
+    }
 
     unsigned sym_err = 0, bit_err = 0;
     const T sigma = T(p.sigma), tx_scale = T(p.tx_scale), rx_scale = T(p.rx_scale);
@@ -705,6 +752,54 @@ ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const cx
                 }
             }   // tx pairs
 
+            if constexpr (kTcShape) {
+                // B operand, element (kk = 2 j + p, n = 8 r8 + 2 e + q), e = 2 t + rx, g' = gbar_j[e] W^(off_r8 d_j):
+                //   p = 0: (g'.re, g'.im)[q];  p = 1: (-g'.im, g'.re)[q].   Layout [hi|lo][k-step][n / 8][k-chunk][n % 8][4 k].
+                // One item per thread: (r8, e, chunk c8) = rows n, n + 1 of one 16-byte K chunk (taps 2 c8, 2 c8 + 1).
+                {
+                    const int e = tid & 3, c8 = (tid >> 2) & 7, r8 = tid >> 5;     // a quarter-warp stores 4 rows x 2 chunks: 2-way conflicts at worst
+                    const int off = 128 * (r8 >> 2) + 256 * (r8 & 3);
+                    cx<T> g[2];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int j = 2 * c8 + h;
+                        g[h] = {0.f, 0.f};
+                        if (j < p.n_taps) {
+                            const float4 gg = gb2[(j * NT + (e >> 1)) * NP];            // (rx0.re, rx1.re, rx0.im, rx1.im)
+                            const cx<T> c = (e & 1) ? cx<T>{gg.y, gg.w} : cx<T>{gg.x, gg.z};
+                            const cx<T> w = tw[(off * p.cls_delay[j]) & (fft - 1)];
+                            // explicit roundings: the fused-RNG and the stream instantiation must agree bit for bit
+                            g[h] = {__fmaf_rn(c.re, w.re, -__fmul_rn(c.im, w.im)), __fmaf_rn(c.re, w.im, __fmul_rn(c.im, w.re))};
+                        }
+                    }
+                    unsigned r0h, r0l, i0h, i0l, r1h, r1l, i1h, i1l;
+                    split_tf32(g[0].re, r0h, r0l); split_tf32(g[0].im, i0h, i0l);
+                    split_tf32(g[1].re, r1h, r1l); split_tf32(g[1].im, i1h, i1l);
+                    constexpr unsigned kNeg = 0x80000000u;
+                    // float4 index of (k-step c8 / 2, n-group r8, chunk c8 % 2, row 2 e) in one part; im row = + 1; lo part = + 512
+                    uint4 *b4 = reinterpret_cast<uint4 *>(bop) + (((c8 >> 1) * 8 + r8) * 2 + (c8 & 1)) * 8 + 2 * e;
+                    b4[0] = make_uint4(r0h, i0h ^ kNeg, r1h, i1h ^ kNeg);             // re row: (g'.re, -g'.im) of taps j, j + 1
+                    b4[1] = make_uint4(i0h, r0h, i1h, r1h);                           // im row: (g'.im,  g'.re)
+                    b4[512] = make_uint4(r0l, i0l ^ kNeg, r1l, i1l ^ kNeg);
+                    b4[513] = make_uint4(i0l, r0l, i1l, r1l);
+                }
+                fence_proxy_async();
+                tc_fence_before();
+                __syncthreads();
+                if (tid == 0) {
+                    tc_fence_after();
+                    constexpr unsigned idesc = umma_idesc_tf32(128, 64);
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+                        const unsigned long long bhi = bdesc0 + (unsigned long long)(ks * 128), blo = bhi + 512ull;     // + bytes / 16
+                        umma_tf32_ts(tmem + 64, tmem + 32 + 8 * ks, bhi, idesc, ks ? 1u : 0u);       // A_lo B_hi
+                        umma_tf32_ts(tmem + 64, tmem + 8 * ks, blo, idesc, 1u);                      // A_hi B_lo
+                        umma_tf32_ts(tmem + 64, tmem + 8 * ks, bhi, idesc, 1u);                      // A_hi B_hi
+                    }
+                    umma_commit(&mbar[2]);
+                }
+            }
+
             // ---------------- F: paired FFT of every rx pair (rotating pool).  When the last pass produces exactly
             // the bins a detection thread owns, it is left to the detection phase (fft_last_pass, from registers).
 #ifndef B200_PAIR_BIG_NU
@@ -757,7 +852,25 @@ ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const cx
                             }
                     }
                 };
-                if constexpr (NU == 4) {
+                bool hk_done = false;
+                if constexpr (kTcShape) {
+                    if (tc) {
+                        mbar_wait(&mbar[2], par_h);          // the 12 MMAs of this frame have completed
+                        par_h ^= 1u;
+                        tc_fence_after();
+                        unsigned v[32];                      // bins tid + 256 u: columns 32 (tid >> 7) + 8 u + 4 t + 2 rx + (re|im)
+                        tmem_ld32(tmem + 64 + (unsigned(tid & 96) << 16) + 32 * (tid >> 7), v);
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+#pragma unroll
+                            for (int t = 0; t < 2; ++t)
+                                Hc[u][t][0] = {pk2(__uint_as_float(v[8 * u + 4 * t]), __uint_as_float(v[8 * u + 4 * t + 2])),
+                                               pk2(__uint_as_float(v[8 * u + 4 * t + 1]), __uint_as_float(v[8 * u + 4 * t + 3]))};
+                        hk_done = true;
+                    }
+                }
+                if (hk_done) {
+                } else if constexpr (NU == 4) {
                     tap_sum(Hc[0], p.cls_start[0], p.cls_start[1]);
                     tap_sum(Hc[2], p.cls_start[1], p.cls_start[2]);
                     tap_sum(Hc[1], p.cls_start[2], p.cls_start[3]);
@@ -900,9 +1013,19 @@ ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const cx
                 }
             }
             if (tma) fence_proxy_async();        // this frame's ordinary stores before the next frame's bulk copies
+            if constexpr (kTcShape) {
+                if (tc) tc_fence_before();       // this frame's TMEM reads before the next frame's MMAs
+            }
             __syncthreads();
         }   // OFDM symbols
     }       // frames
+    if constexpr (kTcShape) {
+        if (tc) {
+            tc_fence_before();
+            __syncthreads();
+            if (tid < 32) tmem_dealloc(tmem, kTmemCols);
+        }
+    }
     flush_counters(sym_err, bit_err, counters);
     if (blockIdx.x == 0 && tid == 0) {
         atomicAdd(&counters[2], (unsigned long long)n_units * p.n_data);
@@ -924,6 +1047,12 @@ inline size_t ofdm_tdl_pair_smem(const OfdmP &p, int M, int NR, int NT) {
     s += al(size_t(NT) * p.used);
     s += 2 * al(sizeof(float) * p.P4);
     return s;
+}
+
+// tensor-core H_k (template parameter TC of the 2x2 / fft 1024 instantiation): at most 16 taps (K = 32), one OFDM symbol
+// per frame (the tx sample buffer is free after the FIR) and room for the 16 KB coefficient operand in it
+inline bool ofdm_tdl_pair_tc_ok(const OfdmP &p) {
+    return p.tc_hk && p.n_taps <= 16 && p.n_sym == 1 && size_t(p.mem + p.S) * sizeof(float4) >= 16384 + 128;
 }
 
 // the pair kernel applies when: float, even Nr/Nt, POLY with one segment, fft % 1024 == 0, mean taps

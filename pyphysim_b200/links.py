@@ -9,6 +9,7 @@ These wrap the ``b200phy_link_*`` entry points of the C ABI.  Two modes:
 ``draw_*`` return the fused-mode draws as tensors in exactly those layouts.
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -41,7 +42,7 @@ class OfdmTdlLink:
     def __init__(self, modulator, fft_size, cp_size, num_used_subcarriers=None, *, num_ofdm_symbols=1,
                  Nr=1, Nt=1, tap_powers_linear, tap_delays, Fd=10.0, Ts=None, L=20, t0=None,
                  noise_var=0.01, filter_noise_var=None, dtype='f32', jakes_mode='auto',
-                 seed=SEED_DEFAULT, use_pair_kernel=True):
+                 seed=SEED_DEFAULT, use_pair_kernel=True, use_tensor_cores=False):
         self.modulator = modulator
         self.dtype = _lib.parse_dtype(dtype)
         used = fft_size if num_used_subcarriers is None else num_used_subcarriers
@@ -65,7 +66,9 @@ class OfdmTdlLink:
         p.noise_var = float(noise_var)
         p.filter_noise_var = float(noise_var if filter_noise_var is None else filter_noise_var)
         p.seed = seed
-        p.reserved = 0 if use_pair_kernel else 1      # bit 0: keep to the generic (non-FFMA2-pair) kernel
+        # bit 0: keep to the generic (non-FFMA2-pair) kernel; bit 1: H_k of the 2x2 / fft-1024 link on the tensor cores
+        # (tcgen05, 3xTF32) instead of the CUDA cores — parity-green but measured 3 % slower, hence opt-in
+        p.reserved = (0 if use_pair_kernel else 1) | (2 if use_tensor_cores or os.environ.get('B200PHY_TC') else 0)
         self.params = p
         self.mem = int(tap_delays[-1])
         self.N = num_ofdm_symbols * (fft_size + cp_size)

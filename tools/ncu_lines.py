@@ -1,13 +1,14 @@
 #!/usr/bin/env python
 """Summarise an .ncu-rep per CUDA source line: instructions executed and stall samples.
-usage: tools/ncu_lines.py report.ncu-rep [top_n]"""
+usage: tools/ncu_lines.py report.ncu-rep [top_n [launch#]]"""
 import csv
 import subprocess
 import sys
 
 rep = sys.argv[1]
 top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
-out = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv', '--print-source', 'cuda,sass'],
+which = sys.argv[3] if len(sys.argv) > 3 else '0'
+out = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv', '--print-source', 'cuda,sass', '--launch-skip', which, '--launch-count', '1'],
                      capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 cur_file, res, seen_kernel = None, [], 0
