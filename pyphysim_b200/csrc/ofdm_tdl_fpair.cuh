@@ -191,12 +191,13 @@ ofdm_tdl_fpair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const c
                         const int q = pr0 + i, j = 2 * q - m0;
                         const uint4 b0 = rng_block(p.seed, STREAM_NOISE, uA, uint64_t(q));
                         const uint4 b1 = rng_block(p.seed, STREAM_NOISE, uB, uint64_t(q));
+                        // unit-variance normals (what the draw kernel stores); sigma is applied by the FIR epilogue's FFMA2
                         if (j >= 0 && j < fft) {
-                            const cx<T> c0 = sigma * cnormal<T>(b0.x, b0.y), c1 = sigma * cnormal<T>(b1.x, b1.y);
+                            const cx<T> c0 = cnormal<T>(b0.x, b0.y), c1 = cnormal<T>(b1.x, b1.y);
                             Y[j] = make_float4(c0.re, c1.re, c0.im, c1.im);
                         }
                         if (j + 1 >= 0 && j + 1 < fft) {
-                            const cx<T> c0 = sigma * cnormal<T>(b0.z, b0.w), c1 = sigma * cnormal<T>(b1.z, b1.w);
+                            const cx<T> c0 = cnormal<T>(b0.z, b0.w), c1 = cnormal<T>(b1.z, b1.w);
                             Y[j + 1] = make_float4(c0.re, c1.re, c0.im, c1.im);
                         }
                     }
@@ -371,8 +372,8 @@ ofdm_tdl_fpair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const c
 #pragma unroll
                         for (int jb = 0; jb < kJBC; ++jb) {
                             const cx<T> n0 = nrow0[tid + jo0 + jb * kOT], n1 = nrow1[tid + jo0 + jb * kOT];
-                            yv[jb].re = add2(mul2(pk2(n0.re, n1.re), sg), sub2(aRR[jb], aII[jb]));
-                            yv[jb].im = add2(mul2(pk2(n0.im, n1.im), sg), add2(aRI[jb], aIR[jb]));
+                            yv[jb].re = fma2(pk2(n0.re, n1.re), sg, sub2(aRR[jb], aII[jb]));
+                            yv[jb].im = fma2(pk2(n0.im, n1.im), sg, add2(aRI[jb], aIR[jb]));
                         }
                     } else if (!FUSED && apipe) {
                         // this thread's raw noise slots have landed: y = sigma * noise + FIR, re-laid as pairs
@@ -381,16 +382,18 @@ ofdm_tdl_fpair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const c
 #pragma unroll
                         for (int jb = 0; jb < kJBC; ++jb) {
                             const float4 v = Y[tid + jo0 + jb * kOT];   // (nA.re, nA.im, nB.re, nB.im)
-                            // rounded product then sum: bit-identical to the fused-RNG path
-                            yv[jb].re = add2(mul2(pk2(v.x, v.z), sg), sub2(aRR[jb], aII[jb]));
-                            yv[jb].im = add2(mul2(pk2(v.y, v.w), sg), add2(aRI[jb], aIR[jb]));
+                            // one fused multiply-add, as in every other mode: bit-identical results
+                            yv[jb].re = fma2(pk2(v.x, v.z), sg, sub2(aRR[jb], aII[jb]));
+                            yv[jb].im = fma2(pk2(v.y, v.w), sg, add2(aRI[jb], aIR[jb]));
                         }
                     } else {
+                        // fused RNG: the buffer holds this symbol's unit-variance normals (lanes = frames)
+                        const u64 sg = pk2(sigma, sigma);
 #pragma unroll
                         for (int jb = 0; jb < kJBC; ++jb) {
                             const ps y = ld_ps(Y + tid + jo0 + jb * kOT);
-                            yv[jb].re = add2(y.re, sub2(aRR[jb], aII[jb]));
-                            yv[jb].im = add2(y.im, add2(aRI[jb], aIR[jb]));
+                            yv[jb].re = fma2(y.re, sg, sub2(aRR[jb], aII[jb]));
+                            yv[jb].im = fma2(y.im, sg, add2(aRI[jb], aIR[jb]));
                         }
                     }
                     if (rx0_fused) {

@@ -490,12 +490,14 @@ ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const cx
                             const int pr = pr0 + i, j = 2 * pr - m0;
                             const uint4 b0 = rng_block(p.seed, STREAM_NOISE, unit, uint64_t(2 * q) * (p.row >> 1) + pr);
                             const uint4 b1 = rng_block(p.seed, STREAM_NOISE, unit, uint64_t(2 * q + 1) * (p.row >> 1) + pr);
+                            // unit-variance normals, exactly what the draw kernel stores: sigma is applied in the FIR
+                            // epilogue by the same single FFMA2 as in stream mode (bit-identical results in both modes)
                             if (j >= 0 && j < fft) {
-                                const cx<T> c0 = sigma * cnormal<T>(b0.x, b0.y), c1 = sigma * cnormal<T>(b1.x, b1.y);
+                                const cx<T> c0 = cnormal<T>(b0.x, b0.y), c1 = cnormal<T>(b1.x, b1.y);
                                 Yp[q][j] = make_float4(c0.re, c1.re, c0.im, c1.im);
                             }
                             if (j + 1 >= 0 && j + 1 < fft) {
-                                const cx<T> c0 = sigma * cnormal<T>(b0.z, b0.w), c1 = sigma * cnormal<T>(b1.z, b1.w);
+                                const cx<T> c0 = cnormal<T>(b0.z, b0.w), c1 = cnormal<T>(b1.z, b1.w);
                                 Yp[q][j + 1] = make_float4(c0.re, c1.re, c0.im, c1.im);
                             }
                         }
@@ -703,8 +705,8 @@ ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const cx
 #pragma unroll
                             for (int jb = 0; jb < kJBC; ++jb) {
                                 const cx<T> n0 = nrow0[tid + jo0 + jb * KT], n1 = nrow1[tid + jo0 + jb * KT];
-                                yv[jb][0].re = add2(mul2(pk2(n0.re, n1.re), sg), aRe[jb][0]);
-                                yv[jb][0].im = add2(mul2(pk2(n0.im, n1.im), sg), aIm[jb][0]);
+                                yv[jb][0].re = fma2(pk2(n0.re, n1.re), sg, aRe[jb][0]);
+                                yv[jb][0].im = fma2(pk2(n0.im, n1.im), sg, aIm[jb][0]);
                             }
                         } else if (!FUSED && apipe && tp == 0) {
                             // the raw noise has landed in this thread's slots: y = sigma * noise + FIR, re-laid as pairs
@@ -715,9 +717,20 @@ ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const cx
 #pragma unroll
                                 for (int q = 0; q < NP; ++q) {
                                     const float4 v = Yp[q][tid + jo0 + jb * KT];       // (n0.re, n0.im, n1.re, n1.im)
-                                    // rounded product then sum: bit-identical to the fused-RNG path
-                                    yv[jb][q].re = add2(mul2(pk2(v.x, v.z), sg), aRe[jb][q]);
-                                    yv[jb][q].im = add2(mul2(pk2(v.y, v.w), sg), aIm[jb][q]);
+                                    // one fused multiply-add, as in every other mode: bit-identical results
+                                    yv[jb][q].re = fma2(pk2(v.x, v.z), sg, aRe[jb][q]);
+                                    yv[jb][q].im = fma2(pk2(v.y, v.w), sg, aIm[jb][q]);
+                                }
+                        } else if (FUSED && tp == 0) {
+                            // fused RNG: the buffer holds this symbol's unit-variance normals (pair layout)
+                            const u64 sg = pk2(sigma, sigma);
+#pragma unroll
+                            for (int jb = 0; jb < kJBC; ++jb)
+#pragma unroll
+                                for (int q = 0; q < NP; ++q) {
+                                    const ps y = ld_ps(Yp[q] + tid + jo0 + jb * KT);
+                                    yv[jb][q].re = fma2(y.re, sg, aRe[jb][q]);
+                                    yv[jb][q].im = fma2(y.im, sg, aIm[jb][q]);
                                 }
                         } else {
 #pragma unroll
