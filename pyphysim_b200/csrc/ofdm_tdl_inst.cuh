@@ -89,8 +89,7 @@ static int launch_pair_kt(const OfdmP &p, const Modem &m, const void *table, uin
                                       (const float *)phi, (const float *)psi, (const cx<float> *)noise,
                                       idx_hat, (cx<float> *)eq_out, (unsigned long long *)counters);
     count_launch();
-    if (TC) note_kernel("ofdm_tdl_pair_kernel<%d,%d,%d,%d,%d,%d,1>", int(FUSED), NR, NT, int(QAMK), KT, LGF);
-    else note_kernel("ofdm_tdl_pair_kernel<%d,%d,%d,%d,%d,%d>", int(FUSED), NR, NT, int(QAMK), KT, LGF);
+    note_kernel("ofdm_tdl_pair_kernel<%d,%d,%d,%d,%d,%d,%d>", int(FUSED), NR, NT, int(QAMK), KT, LGF, int(TC));
     return check_cuda(cudaGetLastError(), "ofdm_tdl_pair_kernel launch");
 }
 

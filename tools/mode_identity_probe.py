@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Repeat the tensor-core (tcgen05 H_k) headline kernel on the same frames: fused vs fused, stream vs stream, fused vs stream."""
+"""Repeat the headline kernel (TC=1: tensor-core H_k variant, TC=0: default) on the same frames: fused vs fused, stream vs
+stream (run-to-run determinism) and fused vs stream (the two modes must agree bit for bit): decisions and equalised samples."""
 import os, sys
 import numpy as np
 import torch
