@@ -82,7 +82,8 @@ ofdm_tdl_fpair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const c
     const bool apipe = !FUSED;
     // TMA input pipeline (see ofdm_tdl_pair.cuh): the noise rows of the two frames as two bulk copies into the rx
     // buffer, the phases of the next pair as four more; one thread issues, completion counted on an mbarrier
-    const bool tma = !FUSED && rx0_fused && mem >= 1 && p.n_sym == 1;
+    // (cp >= 1 or a 16-byte aligned base: the copy of a row that starts 8 bytes off begins one element before it)
+    const bool tma = !FUSED && rx0_fused && mem >= 1 && p.n_sym == 1 && (cp >= 1 || aligned16(noise_g));
     const bool tma_ph = tma && pf16;
     unsigned par_noise = 0, par_phase = 0;
     const cx<T> *nrow0 = nullptr, *nrow1 = nullptr;

@@ -374,7 +374,8 @@ ofdm_tdl_pair_kernel(const __grid_constant__ OfdmP p, const Modem m_in, const cx
     // TMA input pipeline (stream mode, the shapes whose FIR output leaves the landing zone alone): the two noise
     // rows of a symbol are two bulk copies into the rx pair buffer (rows back to back, not interleaved), the phases
     // of the next frame two more; one thread issues them, completion is counted on an mbarrier.
-    const bool tma = !FUSED && rx0_fused && mem >= 1 && p.n_sym == 1;
+    // (cp >= 1 or a 16-byte aligned base: the copy of a row that starts 8 bytes off begins one element before it)
+    const bool tma = !FUSED && rx0_fused && mem >= 1 && p.n_sym == 1 && (cp >= 1 || aligned16(noise_g));
     const bool tma_ph = tma && pf16;
     unsigned par_noise = 0, par_phase = 0;
     const cx<T> *nrow0 = nullptr, *nrow1 = nullptr;

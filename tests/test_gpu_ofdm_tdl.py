@@ -316,14 +316,15 @@ def test_tensor_core_channel_matrices_variant():
 
 
 @pytest.mark.parametrize('ant', [(1, 1), (2, 2)])
-@pytest.mark.parametrize('shift', [0, 1])
-def test_tma_input_pipeline_any_row_alignment(ant, shift):
+@pytest.mark.parametrize('shift,cp', [(0, 72), (1, 72), (1, 0)])
+def test_tma_input_pipeline_any_row_alignment(ant, shift, cp):
     """Stream mode of the two float32 kernels whose noise rows and phases arrive by TMA bulk copies
     (cp.async.bulk + mbarrier, ofdm_tdl_pair.cuh / ofdm_tdl_fpair.cuh): the rows of consecutive frames start
     alternately 0 and 8 bytes off a 16-byte boundary (odd row length), and a sliced noise / phase tensor moves
     everything by one more element — every combination must give the same result bit for bit."""
     import torch
-    cfg, link = make_pair('qam', 64, 1024, 72, 1024, Nr=ant[0], Nt=ant[1], dtype='f32', snr_dB=24.0)
+    # (cp = 0 with a shifted tensor: the first row would have to be copied from before the tensor -> falls back to cp.async)
+    cfg, link = make_pair('qam', 64, 1024, cp, 1024, Nr=ant[0], Nt=ant[1], dtype='f32', snr_dB=24.0)
     n, first = 9, 40
     idx, phi, psi, noise = link.draw(first, n)
     c_f, hat_f = link.run(n, first_unit=first, want_idx=True)
