@@ -85,7 +85,7 @@ typedef struct b200phy_ofdm_tdl_params {
     int32_t struct_size;  /* sizeof(b200phy_ofdm_tdl_params), for ABI checking */
     int32_t dtype;        /* B200PHY_F32 / B200PHY_F64 */
     int32_t fft, cp, used, n_sym; /* OFDM(fft, cp, used) (modulators/ofdm.py:20-94); OFDM symbols/frame */
-    int32_t Nr, Nt;       /* 1x1: one-tap equaliser (ofdm.py:469-552); else Blast (mimo/mimo.py:465-660) */
+    int32_t Nr, Nt;       /* Nt <= Nr <= 4.  1x1: one-tap equaliser (ofdm.py:469-552); else Blast (mimo/mimo.py:465-660) */
     int32_t n_taps;       /* discretised profile (channels/fading.py:272-304) */
     int32_t L;            /* Jakes rays (channels/fading_generators.py:319-351) */
     int32_t jakes_mode;   /* B200PHY_JAKES_* */

@@ -184,10 +184,15 @@ int b200phy_link_ofdm_tdl(const b200phy_ofdm_tdl_params *q, const b200phy_modem 
         B200_DISPATCH(1, 1);
         B200_DISPATCH(2, 1);
         B200_DISPATCH(2, 2);
+        B200_DISPATCH(3, 1);
+        B200_DISPATCH(3, 2);
+        B200_DISPATCH(3, 3);
+        B200_DISPATCH(4, 1);
         B200_DISPATCH(4, 2);
+        B200_DISPATCH(4, 3);
         B200_DISPATCH(4, 4);
         default:
-            set_error("OFDM/TDL link is built for Nr x Nt in {1x1, 2x1, 2x2, 4x2, 4x4}; got %dx%d", q->Nr, q->Nt);
+            set_error("OFDM/TDL link is built for Nt <= Nr <= 4; got %dx%d", q->Nr, q->Nt);
             return B200PHY_ERR_UNSUPPORTED;
     }
 #undef B200_DISPATCH
@@ -199,9 +204,9 @@ int b200phy_ofdm_tdl_check_params(const b200phy_ofdm_tdl_params *q) {
     int e = fill_params(q, m, &p);
     if (e) return e;
     switch (q->Nr * 10 + q->Nt) {
-        case 11: case 21: case 22: case 42: case 44: return B200PHY_OK;
+        case 11: case 21: case 22: case 31: case 32: case 33: case 41: case 42: case 43: case 44: return B200PHY_OK;
         default:
-            set_error("OFDM/TDL link is built for Nr x Nt in {1x1, 2x1, 2x2, 4x2, 4x4}; got %dx%d", q->Nr, q->Nt);
+            set_error("OFDM/TDL link is built for Nt <= Nr <= 4; got %dx%d", q->Nr, q->Nt);
             return B200PHY_ERR_UNSUPPORTED;
     }
 }

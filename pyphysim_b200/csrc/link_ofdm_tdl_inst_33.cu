@@ -1,0 +1,4 @@
+// OFDM/TDL link kernels for Nr=3, Nt=3
+#define B200_NR 3
+#define B200_NT 3
+#include "ofdm_tdl_inst.cuh"

@@ -144,6 +144,11 @@ def test_siso_shapes_f64(case):
     dict(kind='qam', M=16, fft=128, cp=16, used=100, n_sym=2, Nr=2, Nt=1, Fd=400.0, Ts=1e-7),
     dict(kind='qam', M=16, fft=256, cp=18, used=200, Nr=4, Nt=2, snr_dB=15.0),
     dict(kind='qam', M=256, fft=2048, cp=144, used=2048, Nr=4, Nt=4, snr_dB=30.0),          # C5
+    dict(kind='qam', M=16, fft=128, cp=16, used=100, n_sym=2, Nr=3, Nt=1, Fd=300.0, Ts=1e-7),
+    dict(kind='qam', M=16, fft=128, cp=16, used=100, Nr=3, Nt=2, snr_dB=18.0, Fd=300.0, Ts=1e-7),
+    dict(kind='qam', M=64, fft=256, cp=18, used=200, Nr=3, Nt=3, snr_dB=28.0),
+    dict(kind='psk', M=8, fft=128, cp=16, used=100, Nr=4, Nt=1, Fd=300.0, Ts=1e-7),
+    dict(kind='qam', M=16, fft=256, cp=18, used=200, n_sym=2, Nr=4, Nt=3, snr_dB=24.0),
 ])
 def test_mimo_shapes_f64(case):
     cfg, link = make_pair(dtype='f64', **case)
@@ -158,6 +163,8 @@ def test_mimo_shapes_f64(case):
     (dict(kind='qam', M=64, fft=1024, cp=72, used=1024, Nr=2, Nt=2, snr_dB=25.0), 'auto'),
     (dict(kind='qam', M=256, fft=2048, cp=144, used=2048, Nr=4, Nt=4, snr_dB=30.0), 'auto'),
     (dict(kind='qam', M=16, fft=128, cp=16, used=100, n_sym=3, Fd=800.0, Ts=1e-7), 'auto'),
+    (dict(kind='qam', M=16, fft=256, cp=18, used=200, Nr=3, Nt=3, snr_dB=24.0), 'auto'),
+    (dict(kind='qam', M=16, fft=256, cp=18, used=200, Nr=4, Nt=3, snr_dB=24.0), 'auto'),
 ])
 def test_f32_within_tolerance(case, jakes):
     cfg, link = make_pair(dtype='f32', jakes=jakes, **case)
@@ -393,7 +400,7 @@ def test_unsupported_shapes_raise():
     from pyphysim_b200 import links
     pm = product_modem('qam', 16)
     with pytest.raises(NotImplementedError):
-        links.OfdmTdlLink(pm, 64, 16, 52, Nr=3, Nt=3, tap_powers_linear=[1.0], tap_delays=[0]).run(1)
+        links.OfdmTdlLink(pm, 64, 16, 52, Nr=2, Nt=4, tap_powers_linear=[1.0], tap_delays=[0]).run(1)      # Nt > Nr
     with pytest.raises(ValueError):
         links.OfdmTdlLink(pm, 64, 16, 53, tap_powers_linear=[1.0], tap_delays=[0]).run(1)
     with pytest.raises(NotImplementedError):
