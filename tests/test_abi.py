@@ -112,7 +112,7 @@ def test_argument_validation_needs_no_gpu():
     p.struct_size = 8
     assert lib.b200phy_ofdm_tdl_check_params(C.byref(p)) == _lib.ERR_INVALID and b'size mismatch' in lib.b200phy_last_error()
     p.struct_size = C.sizeof(p)
-    p.Nr, p.Nt = 3, 2
+    p.Nr, p.Nt = 2, 3                                     # Nt > Nr is not built (every Nt <= Nr <= 4 is)
     assert lib.b200phy_ofdm_tdl_check_params(C.byref(p)) == _lib.ERR_UNSUPPORTED
     # host entry points validate before touching the device: bad arguments fail here even without a GPU
     cnt64 = (C.c_int64 * 4)()
