@@ -584,7 +584,9 @@ def measure_workload(work, steps, warm, world, quick, sampler=None):
     ms_kernel = timed(work.step, steps, world)         # the dominant kernel alone (no memset / all-reduce)
     for _ in range(warm):
         work.fused()
-    ms_fused = timed(work.fused, steps, world)
+    # auxiliary leg: two timed blocks of K steps, the faster one is kept (a single block has shown 3 % run-to-run
+    # scatter right after the stream legs; the e2e leg below is timed once, through the runner)
+    ms_fused = min(timed(work.fused, steps, world), timed(work.fused, steps, world))
     kernel_fused = lib.b200phy_last_kernel().decode()
     if sampler is not None:
         # short workloads end before nvidia-smi's 50 ms period has produced enough samples: keep the SAME load
