@@ -112,8 +112,11 @@ def test_argument_validation_needs_no_gpu():
     p.struct_size = 8
     assert lib.b200phy_ofdm_tdl_check_params(C.byref(p)) == _lib.ERR_INVALID and b'size mismatch' in lib.b200phy_last_error()
     p.struct_size = C.sizeof(p)
-    p.Nr, p.Nt = 2, 3                                     # Nt > Nr is not built (every Nt <= Nr <= 4 is)
-    assert lib.b200phy_ofdm_tdl_check_params(C.byref(p)) == _lib.ERR_UNSUPPORTED
+    for nr in range(1, 6):                                # every Nt <= Nr <= 4 is built, nothing else
+        for nt in range(1, 6):
+            p.Nr, p.Nt = nr, nt
+            want = 0 if nt <= nr <= 4 else _lib.ERR_UNSUPPORTED
+            assert lib.b200phy_ofdm_tdl_check_params(C.byref(p)) == want, (nr, nt)
     # host entry points validate before touching the device: bad arguments fail here even without a GPU
     cnt64 = (C.c_int64 * 4)()
     p.Nr, p.Nt, p.n_taps = 1, 1, 99
